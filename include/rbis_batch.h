@@ -1,0 +1,180 @@
+/* rbis_batch.h -- C ABI of the B200-native batched RBIS EKF (drop-in boundary).
+ *
+ * One handle = one ensemble of N independent 21-state RBIS filters resident on one B200.  Every
+ * entry point replaces, for a whole ensemble at once, one piece of the reference's per-filter
+ * interface under /root/reference/state-estimator/src/mav_state_est/ (cited per function as
+ * MSE/<file>:<lines>).  Plain pointers and sizes only; no C++/torch types; never throws.
+ *
+ * Conventions
+ *   - All floating point is IEEE double.  Indices are int32, time is int64 microseconds.
+ *   - Ensemble arrays are structure-of-arrays with the FILTER INDEX FASTEST:
+ *       vec  [21][N]   state vector, index layout of RBIS (MSE/rbis.hpp:22-24 + eigen_utils):
+ *                      0-2 angular velocity, 3-5 body velocity, 6-8 chi, 9-11 position,
+ *                      12-14 acceleration, 15-17 gyro bias, 18-20 accel bias
+ *       quat [4][N]    orientation (w,x,y,z)
+ *       cov  [441][N]  RBIM, element (r,c) at row r + 21*c (Eigen column-major, MSE/rbis.hpp:30,123)
+ *       imu  [rows][6][N]  gyro xyz then accelerometer xyz per IMU sample row
+ *       z    [rows][m][N], meas quat [rows][4][N]
+ *   - `mem` says where the caller's ensemble arrays live: host memory (copied by the library on the
+ *     handle's stream; use pinned memory for truly asynchronous copies) or device memory (used in
+ *     place; must stay valid until the call's work has completed).
+ *   - Calls are stream-ordered on the handle and return once enqueued unless stated otherwise;
+ *     rbis_batch_synchronize() waits.  A handle is not thread-safe (the reference is single
+ *     threaded too: MSE/lcm_front_end.cpp:223-229).
+ *   - Return value: 0 on success, negative rbis_status_t on error; rbis_last_error() gives the text.
+ *   - The covariance is kept symmetric-packed on the device (upper triangle of `cov` is read on
+ *     input; both triangles are written on output).  The reference never symmetrises, but its
+ *     covariance is symmetric to rounding by construction.
+ *   - There is no CPU fallback: every compute entry point runs CUDA kernels built for sm_100a and
+ *     fails with RBIS_ERR_CUDA when no such device is present.
+ */
+#ifndef RBIS_BATCH_H_
+#define RBIS_BATCH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBIS_NUM_STATES 21
+#define RBIS_COV_ELEMS 441
+#define RBIS_MAX_MEAS 9      /* largest index set any reference handler emits (SE/gpf/laser_gpf_lib.cpp:108-110) */
+#define RBIS_MAX_STREAMS 8
+#define RBIS_NUM_STATS 96    /* doubles per statistics chunk, see rbis_batch_stats */
+
+typedef struct rbis_batch rbis_batch_t;
+
+typedef enum {
+  RBIS_OK = 0,
+  RBIS_ERR_INVALID = -1,  /* bad argument */
+  RBIS_ERR_CUDA = -2,     /* CUDA runtime failure, or no sm_100 device */
+  RBIS_ERR_ALLOC = -3,
+  RBIS_ERR_STATE = -4     /* call sequence error (e.g. restore of an empty snapshot slot) */
+} rbis_status_t;
+
+typedef enum { RBIS_MEM_HOST = 0, RBIS_MEM_DEVICE = 1 } rbis_mem_t;
+
+/* Fused-program op kinds. */
+typedef enum {
+  RBIS_OP_IMU = 0,       /* RBISIMUProcessStep::updateFilter, MSE/rbis_update_interface.cpp:30-52 */
+  RBIS_OP_MEAS = 1,      /* RBISIndexed[PlusOrientation]Measurement::updateFilter, :54-107 */
+  RBIS_OP_SNAPSHOT = 2,  /* save (state, cov, loglik) of every filter into ring slot `row` */
+  RBIS_OP_RESTORE = 3    /* load them back: the history rewind of MSE/mav_state_est.cpp:35-70 */
+} rbis_op_kind_t;
+
+typedef enum {
+  RBIS_R_SHARED_FULL = 0,      /* one m x m column-major matrix for all filters (HOST pointer always) */
+  RBIS_R_PER_FILTER_DIAG = 1   /* diagonal, [m][N], located as `mem` says */
+} rbis_r_mode_t;
+
+typedef struct {
+  double g_val;            /* eigen_utils g_val, g_vec = (0,0,-g_val); default 9.8 */
+  double chi_tol;          /* eigen_utils chiToQuat tolerance; default 1e-6 */
+  int32_t ctor_folds_chi;  /* RigidBodyState(VectorXd) ctor folds chi into its quaternion; default 1 */
+  int32_t renormalize_quat;/* 0 = reference behaviour (never renormalises, MSE/rbis.cpp:219-227);
+                              1 = renormalise the quaternion after every applied delta */
+  int32_t snapshot_slots;  /* ring slots for RBIS_OP_SNAPSHOT / RESTORE; 0 = none */
+  int32_t device;          /* CUDA device ordinal */
+} rbis_batch_config_t;
+
+/* One measurement stream = the constant part of an RBISIndexedMeasurement /
+ * RBISIndexedPlusOrientationMeasurement constructor (MSE/rbis_update_interface.hpp:90-96,111-117)
+ * plus where its per-row data live. */
+typedef struct {
+  int32_t m;                      /* 1..RBIS_MAX_MEAS */
+  int32_t has_orientation;        /* 0 indexedMeasurement, 1 indexedPlusOrientationMeasurement */
+  int32_t r_mode;                 /* rbis_r_mode_t */
+  int32_t sensor_id;              /* RBISUpdateInterface::sensor_enum value, carried only */
+  int32_t idx[RBIS_MAX_MEAS];     /* state indices, 0..20 */
+  int32_t reserved;
+  const double* z;                /* [rows][m][N]; entries at chi indices are ignored when has_orientation */
+  const double* quat;             /* [rows][4][N] or NULL */
+  const double* R;                /* see rbis_r_mode_t */
+  int64_t rows;
+} rbis_stream_t;
+
+typedef struct {
+  int32_t kind;    /* rbis_op_kind_t */
+  int32_t stream;  /* RBIS_OP_MEAS: stream number */
+  int64_t row;     /* IMU / MEAS: row in the stream; SNAPSHOT / RESTORE: ring slot */
+  int64_t utime;   /* becomes the ensemble's utime (MSE/mav_state_est.cpp:60) */
+  double dt;       /* RBIS_OP_IMU only */
+} rbis_op_t;
+
+const char* rbis_last_error(void);
+void rbis_default_config(rbis_batch_config_t* cfg);
+
+/* ---- lifetime: replaces `new MavStateEstimator(new RBISResetUpdate(...))`, MSE/mav_state_est.cpp:12-22.
+ * The handle owns all device memory; the caller owns every buffer it passes in. */
+int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg);
+int rbis_batch_destroy(rbis_batch_t* h);
+int rbis_batch_synchronize(rbis_batch_t* h);
+int64_t rbis_batch_num_filters(const rbis_batch_t* h);
+/* Raw CUDA stream (cudaStream_t) the handle computes on, for event timing by the caller. */
+void* rbis_batch_stream(rbis_batch_t* h);
+/* Kernels launched by this handle so far (bench.py's gpu_launches). */
+int64_t rbis_batch_launch_count(const rbis_batch_t* h);
+
+/* ---- RBISResetUpdate::updateFilter (MSE/rbis_update_interface.cpp:23-28): posterior := given,
+ * loglikelihood := 0 (or `loglik` [N] when non-NULL).  cov may be NULL to keep the current one. */
+int rbis_batch_set_state(rbis_batch_t* h, const double* vec, const double* quat, const double* cov,
+                         const double* loglik, int64_t utime, int mem);
+/* MavStateEstimator::getHeadState + getMeasurementsLogLikelihood (MSE/mav_state_est.cpp:82-96).
+ * Any output pointer may be NULL.  Synchronises when mem == RBIS_MEM_HOST. */
+int rbis_batch_get_state(rbis_batch_t* h, double* vec, double* quat, double* cov, double* loglik,
+                         int64_t* utime, int mem);
+/* Single-filter (array-of-structures) access for the C++ shim: vec[21], quat[4], cov[441]. Synchronous. */
+int rbis_batch_set_filter(rbis_batch_t* h, int64_t n, const double* vec, const double* quat, const double* cov,
+                          double loglik);
+int rbis_batch_get_filter(rbis_batch_t* h, int64_t n, double* vec, double* quat, double* cov, double* loglik);
+
+/* ---- process noise = the q_* constructor arguments of RBISIMUProcessStep
+ * (MSE/rbis_update_interface.hpp:70-75); variances, as InsHandler squares them
+ * (MSE/sensor_handlers.cpp:18-25).  Either one value for all filters or one per filter. */
+int rbis_batch_set_process_noise(rbis_batch_t* h, double q_gyro, double q_accel, double q_gyro_bias,
+                                 double q_accel_bias);
+int rbis_batch_set_process_noise_per_filter(rbis_batch_t* h, const double* q_gyro, const double* q_accel,
+                                            const double* q_gyro_bias, const double* q_accel_bias, int mem);
+
+/* ---- one update for every filter (each is a one-op fused program) ----
+ * RBISIMUProcessStep::updateFilter: insUpdateState (MSE/rbis.cpp:37-75) + insUpdateCovariance
+ * linearised at the PRIOR state (MSE/rbis.cpp:77-122, rbis_update_interface.cpp:38-39).
+ * gyro/accel: [3][N]. */
+int rbis_batch_ins_step(rbis_batch_t* h, const double* gyro, const double* accel, double dt, int64_t utime,
+                        int mem);
+/* indexedMeasurement + rbisApplyDelta (MSE/rbis.cpp:160-178,219-227).  z [m][N]; R per r_mode. */
+int rbis_batch_indexed_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* R,
+                              int r_mode, int64_t utime, int mem);
+/* indexedPlusOrientationMeasurement + rbisApplyDelta (MSE/rbis.cpp:189-227).  quat [4][N]. */
+int rbis_batch_indexed_orient_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z,
+                                     const double* quat, const double* R, int r_mode, int64_t utime, int mem);
+
+/* ---- the fused hot path: run `n_ops` ops (host array, executed in order) for every filter in ONE
+ * kernel launch, state and covariance resident on chip throughout.  This is the batch form of the
+ * roll-forward loop MSE/mav_state_est.cpp:50-70.  imu may be NULL when no IMU op is present. */
+int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu,
+                         int64_t imu_rows, int n_streams, const rbis_stream_t* streams, int mem);
+
+/* ---- ensemble statistics against a truth state (error definition of
+ * SE/noise_id/noise_id.cpp:37-38; NEES over velocity+chi+position as roll_forward.cpp:54-57).
+ * truth_vec [21] / truth_quat [4] (host) shared by all filters, or per-filter [21][N] / [4][N] (`mem`)
+ * when per_filter != 0.  Filters are reduced in chunks of `chunk` filters (power of two, <= 1024)
+ * in a fixed tree order; out_chunks (host) receives [n_chunks][RBIS_NUM_STATS]:
+ *   [0..20] sum e_i, [21..41] sum e_i^2, [42] sum NEES, [43] sum NEES^2, [44] sum loglik,
+ *   [45] count non-finite filters, [46] count filters, [47] count NEES within the 95% chi2(9) bounds,
+ *   rest reserved (0).
+ * out_per_filter (optional, `mem`): [23][N] = e[21], NEES, loglik per filter.  Synchronous. */
+int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int per_filter,
+                     int chunk, double* out_chunks, int64_t* n_chunks, double* out_per_filter, int mem);
+/* Fixed-order final reduction of chunk partials (ascending chunk index): out[RBIS_NUM_STATS]. */
+int rbis_stats_reduce_chunks(const double* chunks, int64_t n_chunks, double* out);
+
+/* ---- FP64 roofline denominators measured on the handle's device: register-resident independent
+ * DFMA chains, and mma.sync.m8n8k4.f64 (DMMA) for comparison.  TFLOP/s.  Synchronous. */
+int rbis_measure_fp64_peak(int device, int iters, double* dfma_tflops, double* dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBIS_BATCH_H_ */

@@ -1,0 +1,171 @@
+"""ctypes face of the CPU ORACLE (oracle/_build/librbis_oracle.so).
+
+Test infrastructure only (PARITY UNPINNED, see rbis_oracle.hpp): imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by pronto_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "librbis_oracle.so")
+_lib = None
+
+
+class _Stream(C.Structure):
+    _fields_ = [("m", C.c_int32), ("has_orient", C.c_int32), ("r_mode", C.c_int32), ("sensor_id", C.c_int32),
+                ("idx", C.c_int32 * 9), ("_pad", C.c_int32), ("z", C.c_void_p), ("quat", C.c_void_p), ("R", C.c_void_p)]
+
+
+EVENT_DTYPE = np.dtype([("kind", "<i4"), ("stream", "<i4"), ("row", "<i8"), ("utime", "<i8"), ("dt", "<f8")], align=True)
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++, no fast-math)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        lib = C.CDLL(LIB_PATH)
+        vp, d = C.c_void_p, C.c_double
+        lib.orc_set_constants.argtypes = [d, d, C.c_int]
+        lib.orc_linearization.argtypes = [vp, vp, vp]
+        lib.orc_ins_update_state.argtypes = [vp, vp, d, vp, vp]
+        lib.orc_ins_update_covariance.argtypes = [d, d, d, d, vp, vp, vp, d]
+        lib.orc_indexed_measurement.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.orc_indexed_measurement.restype = d
+        lib.orc_apply_delta.argtypes = [vp] * 9
+        lib.orc_subtract_quats.argtypes = [vp, vp, vp]
+        lib.orc_state_error.argtypes = [vp, vp, vp, vp, vp]
+        lib.orc_run_ensemble.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int,
+                                         C.POINTER(_Stream), C.c_int64, vp, C.c_int64, vp, vp, vp, vp]
+        lib.orc_run_ensemble.restype = C.c_int64
+        _lib = lib
+    return _lib
+
+
+def _a(x, n=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if n is not None:
+        assert x.size == n, (x.shape, n)
+    return x
+
+
+def set_constants(g_val=9.8, chi_tol=1e-6, ctor_folds_chi=True):
+    load().orc_set_constants(float(g_val), float(chi_tol), int(bool(ctor_folds_chi)))
+
+
+def linearization(vec, quat):
+    """getIMUProcessLinearizationContinuous -> Ac [21,21]"""
+    vec, quat = _a(vec, 21), _a(quat, 4)
+    Ac = np.empty(441)
+    load().orc_linearization(vec.ctypes.data, quat.ctypes.data, Ac.ctypes.data)
+    return Ac.reshape(21, 21).T.copy()  # column-major -> [r, c]
+
+
+def ins_update_state(gyro, accel, dt, vec, quat):
+    gyro, accel = _a(gyro, 3), _a(accel, 3)
+    vec, quat = _a(vec, 21).copy(), _a(quat, 4).copy()
+    load().orc_ins_update_state(gyro.ctypes.data, accel.ctypes.data, float(dt), vec.ctypes.data, quat.ctypes.data)
+    return vec, quat
+
+
+def ins_update_covariance(q_gyro, q_accel, q_gyro_bias, q_accel_bias, vec, quat, cov, dt):
+    """cov: [21,21] (row, col) -> new [21,21]"""
+    vec, quat = _a(vec, 21), _a(quat, 4)
+    P = np.ascontiguousarray(np.asarray(cov, dtype=np.float64).reshape(21, 21).T).reshape(-1).copy()
+    load().orc_ins_update_covariance(q_gyro, q_accel, q_gyro_bias, q_accel_bias, vec.ctypes.data, quat.ctypes.data,
+                                     P.ctypes.data, float(dt))
+    return P.reshape(21, 21).T.copy()
+
+
+def measurement_update(z, R, idx, vec, quat, cov, meas_quat=None):
+    """indexed[PlusOrientation]Measurement + rbisApplyDelta -> (vec, quat, cov [21,21], loglik term)"""
+    m = len(idx)
+    z, vec, quat = _a(z, m), _a(vec, 21), _a(quat, 4)
+    Rc = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(m, m).T).reshape(-1)
+    idx_a = np.ascontiguousarray(idx, dtype=np.int32)
+    P = np.ascontiguousarray(np.asarray(cov, dtype=np.float64).reshape(21, 21).T).reshape(-1)
+    dvec, dquat, dcov = np.empty(21), np.empty(4), np.empty(441)
+    mq = _a(meas_quat, 4) if meas_quat is not None else None
+    ll = load().orc_indexed_measurement(m, z.ctypes.data, mq.ctypes.data if mq is not None else None, Rc.ctypes.data,
+                                        idx_a.ctypes.data, vec.ctypes.data, quat.ctypes.data, P.ctypes.data,
+                                        dvec.ctypes.data, dquat.ctypes.data, dcov.ctypes.data)
+    pvec, pquat, pcov = np.empty(21), np.empty(4), np.empty(441)
+    load().orc_apply_delta(vec.ctypes.data, quat.ctypes.data, P.ctypes.data, dvec.ctypes.data, dquat.ctypes.data,
+                           dcov.ctypes.data, pvec.ctypes.data, pquat.ctypes.data, pcov.ctypes.data)
+    return pvec, pquat, pcov.reshape(21, 21).T.copy(), ll
+
+
+def subtract_quats(q1, q2):
+    q1, q2 = _a(q1, 4), _a(q2, 4)
+    out = np.empty(3)
+    load().orc_subtract_quats(q1.ctypes.data, q2.ctypes.data, out.ctypes.data)
+    return out
+
+
+def state_error(vec, quat, tvec, tquat):
+    vec, quat, tvec, tquat = _a(vec, 21), _a(quat, 4), _a(tvec, 21), _a(tquat, 4)
+    out = np.empty(21)
+    load().orc_state_error(vec.ctypes.data, quat.ctypes.data, tvec.ctypes.data, tquat.ctypes.data, out.ctypes.data)
+    return out
+
+
+def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events, history_span=10_000_000,
+                 n_threads=1, trace=False):
+    """Replay an ARRIVAL-ordered event list through one MavStateEstimator per filter.
+
+    vec [21][N], quat [4][N], cov [441][N], loglik [N] (copied; results returned).
+    q_params: 4 arrays [N] or scalars.  imu [rows][6][N] or None.
+    streams: list of dicts(idx, z [rows][m][N], R (m x m shared, or [m][N] with per_filter_diag=True),
+             quat [rows][4][N] or None).
+    events: iterable of (kind, stream, row, utime, dt); kind 0 = IMU, 1 = measurement.
+    Returns dict(vec, quat, cov, loglik, calls[, trace_vec, trace_quat, trace_cov, trace_loglik])."""
+    lib = load()
+    vec, quat, cov = _a(vec).copy(), _a(quat).copy(), _a(cov).copy()
+    N = vec.shape[1]
+    loglik = np.zeros(N) if loglik is None else _a(loglik).copy()
+    qs = [np.full(N, float(q)) if np.isscalar(q) else _a(q, N) for q in q_params]
+    ev = np.zeros(len(events), dtype=EVENT_DTYPE)
+    for i, e in enumerate(events):
+        ev[i] = tuple(e)
+    sarr = (_Stream * max(1, len(streams)))()
+    keep = []
+    for s, st in enumerate(streams):
+        m = len(st["idx"])
+        d = sarr[s]
+        d.m, d.has_orient = m, int(st.get("quat") is not None)
+        d.r_mode = 1 if st.get("per_filter_diag") else 0
+        d.sensor_id = int(st.get("sensor_id", 0))
+        for a, i in enumerate(st["idx"]):
+            d.idx[a] = int(i)
+        z = _a(st["z"]); keep.append(z); d.z = z.ctypes.data
+        if st.get("quat") is not None:
+            q = _a(st["quat"]); keep.append(q); d.quat = q.ctypes.data
+        if st.get("per_filter_diag"):
+            R = _a(st["R"], m * N)
+        else:
+            R = np.ascontiguousarray(np.asarray(st["R"], dtype=np.float64).reshape(m, m).T).reshape(-1)
+        keep.append(R); d.R = R.ctypes.data
+    imu_a = _a(imu) if imu is not None else None
+    E = len(ev)
+    tr = [None] * 4
+    if trace:
+        tr = [np.empty((E, 21, N)), np.empty((E, 4, N)), np.empty((E, 441, N)), np.empty((E, N))]
+    calls = lib.orc_run_ensemble(N, int(n_threads), vec.ctypes.data, quat.ctypes.data, cov.ctypes.data,
+                                 loglik.ctypes.data, int(utime0), qs[0].ctypes.data, qs[1].ctypes.data,
+                                 qs[2].ctypes.data, qs[3].ctypes.data,
+                                 imu_a.ctypes.data if imu_a is not None else None, len(streams), sarr, E,
+                                 ev.ctypes.data, int(history_span), *[t.ctypes.data if t is not None else None for t in tr])
+    out = dict(vec=vec, quat=quat, cov=cov, loglik=loglik, calls=int(calls))
+    if trace:
+        out.update(trace_vec=tr[0], trace_quat=tr[1], trace_cov=tr[2], trace_loglik=tr[3])
+    return out

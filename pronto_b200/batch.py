@@ -1,0 +1,276 @@
+"""Thin Python host mirror of the batch API (tests, bench and the multi-GPU driver use it).
+
+All arithmetic happens in librbis_b200.so (CUDA, sm_100a).  Arrays may be numpy (host memory) or
+torch CUDA tensors (device memory, used in place); layouts are those of include/rbis_batch.h
+(structure of arrays, filter index fastest).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+OP_DTYPE = np.dtype([("kind", "<i4"), ("stream", "<i4"), ("row", "<i8"), ("utime", "<i8"), ("dt", "<f8")], align=True)
+assert OP_DTYPE.itemsize == C.sizeof(capi.Op)
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a, shape=None, name="array"):
+    """(address, mem) of a float64 contiguous numpy array or torch CUDA tensor."""
+    if a is None:
+        return None, None
+    if _is_torch(a):
+        import torch
+
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            raise ValueError(f"{name}: need a contiguous float64 tensor")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: shape {tuple(a.shape)} != {tuple(shape)}")
+        return a.data_ptr(), (capi.MEM_DEVICE if a.is_cuda else capi.MEM_HOST)
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags.c_contiguous:
+        raise ValueError(f"{name}: need a C-contiguous float64 numpy array")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: shape {a.shape} != {tuple(shape)}")
+    return a.ctypes.data, capi.MEM_HOST
+
+
+def _common_mem(mems, what):
+    mems = [m for m in mems if m is not None]
+    if not mems:
+        return capi.MEM_HOST
+    if any(m != mems[0] for m in mems):
+        raise ValueError(f"{what}: all arrays of one call must live in the same memory space")
+    return mems[0]
+
+
+class MeasStream:
+    """Constant part + data of an RBISIndexed[PlusOrientation]Measurement stream
+    (MSE/rbis_update_interface.hpp:84-120): index set, z rows, R, optional orientation rows."""
+
+    def __init__(self, idx, z, R, quat=None, per_filter_diag=False, sensor_id=0):
+        self.idx = [int(i) for i in idx]
+        self.z, self.R, self.quat = z, R, quat
+        self.per_filter_diag = bool(per_filter_diag)
+        self.sensor_id = int(sensor_id)
+
+
+def make_ops(entries):
+    """entries: iterable of (kind, stream, row, utime, dt) -> structured numpy op array."""
+    entries = list(entries)
+    ops = np.zeros(len(entries), dtype=OP_DTYPE)
+    for i, (kind, stream, row, utime, dt) in enumerate(entries):
+        ops[i] = (kind, stream, row, utime, dt)
+    return ops
+
+
+class RBISBatch:
+    """An ensemble of N RBIS filters on one GPU (rbis_batch_t)."""
+
+    def __init__(self, n_filters, device=0, g_val=9.8, chi_tol=1e-6, ctor_folds_chi=True, renormalize_quat=False,
+                 snapshot_slots=0):
+        self.lib = capi.load()
+        cfg = capi.Config()
+        self.lib.rbis_default_config(C.byref(cfg))
+        cfg.g_val, cfg.chi_tol = float(g_val), float(chi_tol)
+        cfg.ctor_folds_chi, cfg.renormalize_quat = int(bool(ctor_folds_chi)), int(bool(renormalize_quat))
+        cfg.snapshot_slots, cfg.device = int(snapshot_slots), int(device)
+        self.h = C.c_void_p()
+        capi.check(self.lib.rbis_batch_create(C.byref(self.h), int(n_filters), C.byref(cfg)))
+        self.N = int(n_filters)
+        self.device = int(device)
+        self._keep = []  # arrays that must outlive asynchronous calls
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.rbis_batch_destroy(self.h)
+            self.h = C.c_void_p()
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- state ----
+    def set_state(self, vec, quat, cov=None, loglik=None, utime=0):
+        N = self.N
+        pv, m1 = _ptr(vec, (21, N), "vec")
+        pq, m2 = _ptr(quat, (4, N), "quat")
+        pc, m3 = _ptr(cov, (441, N), "cov")
+        pl, m4 = _ptr(loglik, (N,), "loglik")
+        mem = _common_mem([m1, m2, m3, m4], "set_state")
+        capi.check(self.lib.rbis_batch_set_state(self.h, pv, pq, pc, pl, int(utime), mem))
+
+    def get_state(self, cov=True):
+        """-> (vec [21][N], quat [4][N], cov [441][N] or None, loglik [N], utime) as numpy."""
+        N = self.N
+        vec = np.empty((21, N)); quat = np.empty((4, N)); ll = np.empty(N)
+        P = np.empty((441, N)) if cov else None
+        ut = C.c_int64(0)
+        capi.check(self.lib.rbis_batch_get_state(self.h, vec.ctypes.data, quat.ctypes.data,
+                                                 P.ctypes.data if cov else None, ll.ctypes.data, C.byref(ut),
+                                                 capi.MEM_HOST))
+        return vec, quat, P, ll, ut.value
+
+    def get_state_into(self, vec=None, quat=None, cov=None, loglik=None):
+        """Device or host destination arrays (torch CUDA tensors or numpy); any may be None."""
+        N = self.N
+        pv, m1 = _ptr(vec, (21, N), "vec")
+        pq, m2 = _ptr(quat, (4, N), "quat")
+        pc, m3 = _ptr(cov, (441, N), "cov")
+        pl, m4 = _ptr(loglik, (N,), "loglik")
+        mem = _common_mem([m1, m2, m3, m4], "get_state_into")
+        ut = C.c_int64(0)
+        capi.check(self.lib.rbis_batch_get_state(self.h, pv, pq, pc, pl, C.byref(ut), mem))
+        return ut.value
+
+    def set_filter(self, n, vec, quat, cov, loglik=0.0):
+        vec = np.ascontiguousarray(vec, dtype=np.float64); quat = np.ascontiguousarray(quat, dtype=np.float64)
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        assert vec.size == 21 and quat.size == 4 and cov.size == 441
+        capi.check(self.lib.rbis_batch_set_filter(self.h, int(n), vec.ctypes.data, quat.ctypes.data, cov.ctypes.data,
+                                                  float(loglik)))
+
+    def get_filter(self, n):
+        vec = np.empty(21); quat = np.empty(4); cov = np.empty(441); ll = C.c_double(0)
+        capi.check(self.lib.rbis_batch_get_filter(self.h, int(n), vec.ctypes.data, quat.ctypes.data, cov.ctypes.data,
+                                                  C.byref(ll)))
+        return vec, quat, cov, ll.value
+
+    def set_process_noise(self, q_gyro, q_accel, q_gyro_bias, q_accel_bias):
+        args = [q_gyro, q_accel, q_gyro_bias, q_accel_bias]
+        if all(np.isscalar(a) for a in args):
+            capi.check(self.lib.rbis_batch_set_process_noise(self.h, *[float(a) for a in args]))
+            return
+        ptrs, mems = [], []
+        for a in args:
+            if np.isscalar(a):
+                a = np.full(self.N, float(a))
+            p, m = _ptr(a, (self.N,), "q")
+            ptrs.append(p); mems.append(m)
+        capi.check(self.lib.rbis_batch_set_process_noise_per_filter(self.h, *ptrs, _common_mem(mems, "process noise")))
+
+    # ---- single updates ----
+    def ins_step(self, gyro, accel, dt, utime=0):
+        pg, m1 = _ptr(gyro, (3, self.N), "gyro")
+        pa, m2 = _ptr(accel, (3, self.N), "accel")
+        capi.check(self.lib.rbis_batch_ins_step(self.h, pg, pa, float(dt), int(utime), _common_mem([m1, m2], "ins_step")))
+
+    def indexed_update(self, idx, z, R, utime=0, quat=None, per_filter_diag=False):
+        m = len(idx)
+        idx_a = (C.c_int32 * m)(*[int(i) for i in idx])
+        pz, m1 = _ptr(z, (m, self.N), "z")
+        if per_filter_diag:
+            pr, m2 = _ptr(R, (m, self.N), "R")
+        else:
+            R = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(m, m).T)  # column-major m x m
+            pr, m2 = R.ctypes.data, None
+        r_mode = capi.R_PER_FILTER_DIAG if per_filter_diag else capi.R_SHARED_FULL
+        if quat is None:
+            mem = _common_mem([m1, m2], "indexed_update")
+            capi.check(self.lib.rbis_batch_indexed_update(self.h, m, idx_a, pz, pr, r_mode, int(utime), mem))
+        else:
+            pq, m3 = _ptr(quat, (4, self.N), "quat")
+            mem = _common_mem([m1, m2, m3], "indexed_orient_update")
+            capi.check(self.lib.rbis_batch_indexed_orient_update(self.h, m, idx_a, pz, pq, pr, r_mode, int(utime), mem))
+
+    # ---- fused program ----
+    def run_fused(self, ops, imu=None, streams=()):
+        """ops: structured array (OP_DTYPE) or iterable of (kind, stream, row, utime, dt)."""
+        if not (isinstance(ops, np.ndarray) and ops.dtype == OP_DTYPE):
+            ops = make_ops(ops)
+        ops = np.ascontiguousarray(ops)
+        mems = []
+        p_imu, imu_rows = None, 0
+        if imu is not None:
+            if imu.ndim != 3 or tuple(imu.shape[1:]) != (6, self.N):
+                raise ValueError("imu must be [rows][6][N]")
+            p_imu, mm = _ptr(imu, name="imu")
+            imu_rows = int(imu.shape[0]); mems.append(mm)
+        sarr = (capi.Stream * max(1, len(streams)))()
+        keep = [ops, imu]
+        for s, st in enumerate(streams):
+            m = len(st.idx)
+            d = sarr[s]
+            d.m, d.has_orientation, d.sensor_id = m, int(st.quat is not None), st.sensor_id
+            d.r_mode = capi.R_PER_FILTER_DIAG if st.per_filter_diag else capi.R_SHARED_FULL
+            for a, i in enumerate(st.idx):
+                d.idx[a] = i
+            if st.z.ndim != 3 or tuple(st.z.shape[1:]) != (m, self.N):
+                raise ValueError(f"stream {s}: z must be [rows][{m}][N]")
+            d.rows = int(st.z.shape[0])
+            d.z, mm = _ptr(st.z, name="z"); mems.append(mm)
+            if st.quat is not None:
+                if tuple(st.quat.shape) != (d.rows, 4, self.N):
+                    raise ValueError(f"stream {s}: quat must be [rows][4][N]")
+                d.quat, mm = _ptr(st.quat, name="quat"); mems.append(mm)
+            if st.per_filter_diag:
+                d.R, mm = _ptr(st.R, (m, self.N), "R"); mems.append(mm)
+            else:
+                R = np.ascontiguousarray(np.asarray(st.R, dtype=np.float64).reshape(m, m).T)
+                keep.append(R)
+                d.R = R.ctypes.data
+            keep.append(st)
+        mem = _common_mem(mems, "run_fused")
+        # host inputs must outlive their asynchronous copies: hold the last few calls' arrays
+        self._keep_ring = (getattr(self, "_keep_ring", []) + [keep])[-4:]
+        capi.check(self.lib.rbis_batch_run_fused(self.h, len(ops), ops.ctypes.data_as(C.POINTER(capi.Op)), p_imu,
+                                                 imu_rows, len(streams), sarr, mem))
+
+    def synchronize(self):
+        capi.check(self.lib.rbis_batch_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.rbis_batch_launch_count(self.h))
+
+    @property
+    def cuda_stream(self):
+        return int(self.lib.rbis_batch_stream(self.h) or 0)
+
+    # ---- statistics ----
+    def stats(self, truth_vec, truth_quat, chunk=1024, per_filter_truth=False, want_per_filter=False):
+        """-> (chunks [n_chunks][96], per_filter [23][N] or None).  See rbis_batch_stats."""
+        N = self.N
+        n_chunks = (N + chunk - 1) // chunk
+        out = np.zeros((n_chunks, capi.NUM_STATS))
+        pf = np.empty((23, N)) if want_per_filter else None
+        if per_filter_truth:
+            pv, m1 = _ptr(truth_vec, (21, N), "truth_vec"); pq, m2 = _ptr(truth_quat, (4, N), "truth_quat")
+            mem = _common_mem([m1, m2], "stats")
+            if mem != capi.MEM_HOST:
+                raise ValueError("stats: per-filter truth must be host arrays in this wrapper")
+        else:
+            tv = np.ascontiguousarray(truth_vec, dtype=np.float64); tq = np.ascontiguousarray(truth_quat, dtype=np.float64)
+            assert tv.size == 21 and tq.size == 4
+            pv, pq, mem = tv.ctypes.data, tq.ctypes.data, capi.MEM_HOST
+        nch = C.c_int64(0)
+        capi.check(self.lib.rbis_batch_stats(self.h, pv, pq, int(per_filter_truth), int(chunk), out.ctypes.data,
+                                             C.byref(nch), pf.ctypes.data if want_per_filter else None, mem))
+        assert nch.value == n_chunks
+        return out, pf
+
+
+def reduce_chunks(chunks):
+    """Fixed ascending-order sum of chunk partials -> [96] (rbis_stats_reduce_chunks)."""
+    chunks = np.ascontiguousarray(chunks, dtype=np.float64)
+    out = np.zeros(capi.NUM_STATS)
+    capi.check(capi.load().rbis_stats_reduce_chunks(chunks.ctypes.data, chunks.shape[0], out.ctypes.data))
+    return out
+
+
+def measure_fp64_peak(device=0, iters=2000):
+    """-> (dfma_tflops, dmma_tflops) measured on `device`."""
+    a, b = C.c_double(0), C.c_double(0)
+    capi.check(capi.load().rbis_measure_fp64_peak(int(device), int(iters), C.byref(a), C.byref(b)))
+    return a.value, b.value

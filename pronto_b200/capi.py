@@ -1,0 +1,116 @@
+"""ctypes binding of librbis_b200.so (the C ABI declared in include/rbis_batch.h).
+
+This module only loads the library and declares prototypes; it performs no arithmetic.  If the
+shared library is missing it raises: there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librbis_b200.so")
+
+NUM_STATES = 21
+COV_ELEMS = 441
+MAX_MEAS = 9
+MAX_STREAMS = 8
+NUM_STATS = 96
+
+MEM_HOST, MEM_DEVICE = 0, 1
+OP_IMU, OP_MEAS, OP_SNAPSHOT, OP_RESTORE = 0, 1, 2, 3
+R_SHARED_FULL, R_PER_FILTER_DIAG = 0, 1
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("g_val", C.c_double),
+        ("chi_tol", C.c_double),
+        ("ctor_folds_chi", C.c_int32),
+        ("renormalize_quat", C.c_int32),
+        ("snapshot_slots", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+class Stream(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32),
+        ("has_orientation", C.c_int32),
+        ("r_mode", C.c_int32),
+        ("sensor_id", C.c_int32),
+        ("idx", C.c_int32 * MAX_MEAS),
+        ("reserved", C.c_int32),
+        ("z", C.c_void_p),
+        ("quat", C.c_void_p),
+        ("R", C.c_void_p),
+        ("rows", C.c_int64),
+    ]
+
+
+class Op(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("stream", C.c_int32),
+        ("row", C.c_int64),
+        ("utime", C.c_int64),
+        ("dt", C.c_double),
+    ]
+
+
+# every symbol include/rbis_batch.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "rbis_last_error": (C.c_char_p, []),
+    "rbis_default_config": (None, [C.POINTER(Config)]),
+    "rbis_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.POINTER(Config)]),
+    "rbis_batch_destroy": (C.c_int, [C.c_void_p]),
+    "rbis_batch_synchronize": (C.c_int, [C.c_void_p]),
+    "rbis_batch_num_filters": (C.c_int64, [C.c_void_p]),
+    "rbis_batch_stream": (C.c_void_p, [C.c_void_p]),
+    "rbis_batch_launch_count": (C.c_int64, [C.c_void_p]),
+    "rbis_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "rbis_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),
+    "rbis_batch_set_filter": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
+    "rbis_batch_get_filter": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_double_p]),
+    "rbis_batch_set_process_noise": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "rbis_batch_set_process_noise_per_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "rbis_batch_ins_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int]),
+    "rbis_batch_indexed_update": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
+    "rbis_batch_indexed_orient_update": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
+    "rbis_batch_run_fused": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Op), C.c_void_p, C.c_int64, C.c_int, C.POINTER(Stream), C.c_int]),
+    "rbis_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_int64_p, C.c_void_p, C.c_int]),
+    "rbis_stats_reduce_chunks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "rbis_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load librbis_b200.so (built by __graft_entry__.build()); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "pronto_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class RBISError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise RBISError(f"rbis error {rc}: {load().rbis_last_error().decode()}")

@@ -1,0 +1,636 @@
+// rbis_batch.cu -- host side of librbis_b200.so: the extern "C" batch API of include/rbis_batch.h
+// over the sm_100a kernels in rbis_kernels.cuh / rbis_stats.cuh.  No CPU compute path exists here:
+// every entry point that updates filters launches a CUDA kernel or fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rbis_batch.h"
+#include "rbis_kernels.cuh"
+#include "rbis_stats.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(RBIS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {  // grow-only device buffer
+  double* p = nullptr;
+  size_t cap = 0;  // doubles
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    cap = n;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct StagingSlot {  // device copies of caller-host input arrays for one fused run
+  DevBuf imu;
+  DevBuf z[RBIS_MAX_STREAMS], quat[RBIS_MAX_STREAMS], rdiag[RBIS_MAX_STREAMS];
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+};
+
+}  // namespace
+
+struct rbis_batch {
+  int64_t N = 0;
+  rbis_batch_config_t cfg{};
+  int64_t utime = 0;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // host->device input staging
+  double *vec = nullptr, *quat = nullptr, *P = nullptr, *loglik = nullptr;
+  double* qparams = nullptr;  // [4][N]
+  double* snap = nullptr;
+  std::vector<char> snap_valid;
+  DevBuf full_cov;      // [441][N] scratch for set/get_state
+  DevBuf misc;          // small scratch
+  rbisk::Op* d_ops = nullptr;
+  size_t d_ops_cap = 0;
+  double* d_rshared = nullptr;  // [MAX_STREAMS][81]
+  StagingSlot slots[2];
+  int slot_toggle = 0;
+  int smem_bytes = 0;
+};
+
+namespace {
+
+constexpr int kSmemBytes = (rbisk::NP - rbisk::NPW) * rbisk::TPB * (int)sizeof(double);
+
+int use_device(const rbis_batch* h) {
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail(RBIS_ERR_CUDA, "cudaSetDevice(%d): %s", h->cfg.device, cudaGetErrorString(e));
+  return 0;
+}
+
+// Split the m rows of a measurement into consecutive chunks along which R is block diagonal, then
+// merge neighbours greedily up to 3 rows (the register-resident fast path).  Blocks wider than 3
+// stay whole and take the general path.
+void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) {
+  std::vector<int> cut;  // start indices of finest blocks
+  cut.push_back(0);
+  for (int k = 1; k < m; k++) {
+    bool sep = true;
+    if (r_mode == RBIS_R_SHARED_FULL) {
+      for (int a = 0; a < k && sep; a++)
+        for (int b = k; b < m; b++)
+          if (R_host[a + m * b] != 0.0 || R_host[b + m * a] != 0.0) { sep = false; break; }
+    }
+    if (sep) cut.push_back(k);
+  }
+  cut.push_back(m);
+  d.n_chunks = 0;
+  int start = 0, len = 0;
+  for (size_t i = 0; i + 1 < cut.size(); i++) {
+    const int blen = cut[i + 1] - cut[i];
+    if (len > 0 && len + blen > 3) {
+      d.chunk_start[d.n_chunks] = start;
+      d.chunk_len[d.n_chunks++] = len;
+      len = 0;
+    }
+    if (len == 0) start = cut[i];
+    len += blen;
+  }
+  if (len > 0) {
+    d.chunk_start[d.n_chunks] = start;
+    d.chunk_len[d.n_chunks++] = len;
+  }
+}
+
+int copy_in(rbis_batch* h, DevBuf& buf, const double* src, size_t count, int mem, cudaStream_t st,
+            const double** out) {
+  if (mem == RBIS_MEM_DEVICE) {
+    *out = src;
+    return 0;
+  }
+  if (buf.ensure(count)) return fail(RBIS_ERR_ALLOC, "device staging allocation of %zu doubles failed", count);
+  CUDA_TRY(cudaMemcpyAsync(buf.p, src, count * sizeof(double), cudaMemcpyHostToDevice, st));
+  *out = buf.p;
+  (void)h;
+  return 0;
+}
+
+int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
+                 int n_streams, const rbis_stream_t* streams, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(RBIS_ERR_INVALID, "bad op list");
+  if (n_streams < 0 || n_streams > RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "n_streams out of range");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (n_ops == 0) return 0;
+  if (int rc = use_device(h)) return rc;
+  const int64_t N = h->N;
+
+  // ---- validate ops and translate ----
+  std::vector<rbisk::Op> kops((size_t)n_ops);
+  std::vector<char> snap_valid = h->snap_valid;
+  int64_t last_utime = h->utime;
+  for (int64_t i = 0; i < n_ops; i++) {
+    const rbis_op_t& o = ops[i];
+    rbisk::Op& k = kops[(size_t)i];
+    k.kind = o.kind; k.stream = o.stream; k.row = o.row; k.dt = o.dt;
+    switch (o.kind) {
+      case RBIS_OP_IMU:
+        if (!imu) return fail(RBIS_ERR_INVALID, "op %lld is an IMU op but imu is NULL", (long long)i);
+        if (o.row < 0 || o.row >= imu_rows) return fail(RBIS_ERR_INVALID, "op %lld: imu row %lld out of range", (long long)i, (long long)o.row);
+        if (!(o.dt > 0)) return fail(RBIS_ERR_INVALID, "op %lld: dt must be positive", (long long)i);
+        last_utime = o.utime;
+        break;
+      case RBIS_OP_MEAS:
+        if (o.stream < 0 || o.stream >= n_streams) return fail(RBIS_ERR_INVALID, "op %lld: stream %d out of range", (long long)i, o.stream);
+        if (o.row < 0 || o.row >= streams[o.stream].rows) return fail(RBIS_ERR_INVALID, "op %lld: row %lld out of range for stream %d", (long long)i, (long long)o.row, o.stream);
+        last_utime = o.utime;
+        break;
+      case RBIS_OP_SNAPSHOT:
+        if (o.row < 0 || o.row >= h->cfg.snapshot_slots) return fail(RBIS_ERR_INVALID, "op %lld: snapshot slot %lld out of range (%d slots)", (long long)i, (long long)o.row, h->cfg.snapshot_slots);
+        snap_valid[(size_t)o.row] = 1;
+        break;
+      case RBIS_OP_RESTORE:
+        if (o.row < 0 || o.row >= h->cfg.snapshot_slots) return fail(RBIS_ERR_INVALID, "op %lld: snapshot slot %lld out of range (%d slots)", (long long)i, (long long)o.row, h->cfg.snapshot_slots);
+        if (!snap_valid[(size_t)o.row]) return fail(RBIS_ERR_STATE, "op %lld: restore of empty snapshot slot %lld", (long long)i, (long long)o.row);
+        last_utime = o.utime;
+        break;
+      default:
+        return fail(RBIS_ERR_INVALID, "op %lld: unknown kind %d", (long long)i, o.kind);
+    }
+  }
+
+  rbisk::KParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.N = N;
+  kp.vec = h->vec; kp.quat = h->quat; kp.P = h->P; kp.loglik = h->loglik;
+  kp.q_gyro = h->qparams; kp.q_accel = h->qparams + N; kp.q_gyro_bias = h->qparams + 2 * N;
+  kp.q_accel_bias = h->qparams + 3 * N;
+  kp.snap = h->snap;
+  kp.n_snap = h->cfg.snapshot_slots;
+  kp.n_ops = n_ops;
+  kp.g_val = h->cfg.g_val; kp.chi_tol = h->cfg.chi_tol;
+  kp.ctor_folds_chi = h->cfg.ctor_folds_chi; kp.renorm = h->cfg.renormalize_quat;
+
+  // ---- inputs: stage host arrays on the copy stream (double buffered), or use device arrays in place ----
+  StagingSlot& slot = h->slots[h->slot_toggle];
+  h->slot_toggle ^= 1;
+  cudaStream_t cst = h->copy_stream;
+  const bool staging = (mem == RBIS_MEM_HOST);
+  if (staging) CUDA_TRY(cudaStreamWaitEvent(cst, slot.consumed, 0));
+  if (imu) {
+    if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * N, mem, cst, &kp.imu)) return rc;
+  }
+  std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * 81, 0.0);
+  bool any_shared = false;
+  for (int s = 0; s < n_streams; s++) {
+    const rbis_stream_t& in = streams[s];
+    rbisk::StreamDesc& d = kp.streams[s];
+    if (in.m < 1 || in.m > RBIS_MAX_MEAS) return fail(RBIS_ERR_INVALID, "stream %d: m=%d out of range", s, in.m);
+    for (int a = 0; a < in.m; a++)
+      if (in.idx[a] < 0 || in.idx[a] >= RBIS_NUM_STATES) return fail(RBIS_ERR_INVALID, "stream %d: index %d out of range", s, in.idx[a]);
+    if (in.rows < 0) return fail(RBIS_ERR_INVALID, "stream %d: negative rows", s);
+    if (in.rows > 0 && (!in.z || !in.R)) return fail(RBIS_ERR_INVALID, "stream %d: z and R are required", s);
+    if (in.has_orientation && in.rows > 0 && !in.quat) return fail(RBIS_ERR_INVALID, "stream %d: has_orientation but quat is NULL", s);
+    if (in.r_mode != RBIS_R_SHARED_FULL && in.r_mode != RBIS_R_PER_FILTER_DIAG) return fail(RBIS_ERR_INVALID, "stream %d: bad r_mode", s);
+    d.m = in.m; d.has_orient = in.has_orientation ? 1 : 0; d.r_mode = in.r_mode;
+    for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
+    if (in.rows == 0) { d.n_chunks = 0; continue; }
+    plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
+    if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * N, mem, cst, &d.z)) return rc;
+    if (in.has_orientation)
+      if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * N, mem, cst, &d.quat)) return rc;
+    if (in.r_mode == RBIS_R_SHARED_FULL) {
+      std::memcpy(&rshared[(size_t)s * 81], in.R, sizeof(double) * in.m * in.m);
+      d.R = h->d_rshared + (size_t)s * 81;
+      any_shared = true;
+    } else {
+      if (int rc = copy_in(h, slot.rdiag[s], in.R, (size_t)in.m * N, mem, cst, &d.R)) return rc;
+    }
+  }
+  if (staging) {
+    CUDA_TRY(cudaEventRecord(slot.copied, cst));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
+  }
+
+  // ---- op table and shared R matrices (small, pageable source: staged synchronously by the runtime) ----
+  if ((size_t)n_ops > h->d_ops_cap) {
+    if (h->d_ops) {
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_ops);
+      h->d_ops = nullptr;
+      h->d_ops_cap = 0;
+    }
+    size_t cap = (size_t)n_ops * 2;
+    if (cap < 1024) cap = 1024;
+    CUDA_TRY(cudaMalloc(&h->d_ops, cap * sizeof(rbisk::Op)));
+    h->d_ops_cap = cap;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->stream));
+  if (any_shared)
+    CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  kp.ops = h->d_ops;
+
+  const unsigned grid = (unsigned)((N + rbisk::TPB - 1) / rbisk::TPB);
+  rbisk::rbis_fused_kernel<<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
+  h->snap_valid = snap_valid;
+  h->utime = last_utime;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rbis_last_error(void) { return g_last_error.c_str(); }
+
+void rbis_default_config(rbis_batch_config_t* cfg) {
+  if (!cfg) return;
+  cfg->g_val = 9.8;
+  cfg->chi_tol = 1e-6;
+  cfg->ctor_folds_chi = 1;
+  cfg->renormalize_quat = 0;
+  cfg->snapshot_slots = 0;
+  cfg->device = 0;
+}
+
+int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
+  if (!out) return fail(RBIS_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_filters <= 0) return fail(RBIS_ERR_INVALID, "n_filters must be positive");
+  rbis_batch_config_t c;
+  if (cfg) c = *cfg; else rbis_default_config(&c);
+  if (c.snapshot_slots < 0) return fail(RBIS_ERR_INVALID, "snapshot_slots must be >= 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(RBIS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(RBIS_ERR_INVALID, "device %d out of range (%d devices)", c.device, ndev);
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10)
+    return fail(RBIS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
+  if ((int)prop.sharedMemPerBlockOptin < kSmemBytes)
+    return fail(RBIS_ERR_CUDA, "device offers %zu B shared memory per block, %d needed", prop.sharedMemPerBlockOptin, kSmemBytes);
+
+  rbis_batch* h = new (std::nothrow) rbis_batch();
+  if (!h) return fail(RBIS_ERR_ALLOC, "host allocation failed");
+  h->N = n_filters;
+  h->cfg = c;
+  h->smem_bytes = kSmemBytes;
+  const size_t N = (size_t)n_filters;
+  auto cleanup = [&](int code) { rbis_batch_destroy(h); return code; };
+#define CREATE_TRY(expr)                                                                             \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      fail(_e == cudaErrorMemoryAllocation ? RBIS_ERR_ALLOC : RBIS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+      cudaGetLastError();                                                                            \
+      return cleanup(_e == cudaErrorMemoryAllocation ? RBIS_ERR_ALLOC : RBIS_ERR_CUDA);              \
+    }                                                                                                \
+  } while (0)
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& s : h->slots) {
+    CREATE_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+  }
+  CREATE_TRY(cudaMalloc(&h->vec, N * 21 * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->quat, N * 4 * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->P, N * rbisk::NP * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->loglik, N * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->qparams, N * 4 * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->d_rshared, (size_t)RBIS_MAX_STREAMS * 81 * sizeof(double)));
+  if (c.snapshot_slots > 0) {
+    CREATE_TRY(cudaMalloc(&h->snap, (size_t)c.snapshot_slots * 257 * N * sizeof(double)));
+    h->snap_valid.assign((size_t)c.snapshot_slots, 0);
+  }
+  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  // default state: zeros, identity quaternion, zero covariance, zero process noise
+  CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
+  CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));
+  rbisk::fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->quat, 1.0, (long long)N);
+  CREATE_TRY(cudaGetLastError());
+  CREATE_TRY(cudaMemsetAsync(h->P, 0, N * rbisk::NP * sizeof(double), h->stream));
+  CREATE_TRY(cudaMemsetAsync(h->loglik, 0, N * sizeof(double), h->stream));
+  CREATE_TRY(cudaMemsetAsync(h->qparams, 0, N * 4 * sizeof(double), h->stream));
+  CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+  *out = h;
+  return 0;
+}
+
+int rbis_batch_destroy(rbis_batch_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
+  cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared);
+  h->full_cov.release(); h->misc.release();
+  for (auto& s : h->slots) {
+    s.imu.release();
+    for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  cudaGetLastError();
+  delete h;
+  return 0;
+}
+
+int rbis_batch_synchronize(rbis_batch_t* h) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (int rc = use_device(h)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t rbis_batch_num_filters(const rbis_batch_t* h) { return h ? h->N : 0; }
+void* rbis_batch_stream(rbis_batch_t* h) { return h ? (void*)h->stream : nullptr; }
+int64_t rbis_batch_launch_count(const rbis_batch_t* h) { return h ? h->launches : 0; }
+
+int rbis_batch_set_state(rbis_batch_t* h, const double* vec, const double* quat, const double* cov,
+                         const double* loglik, int64_t utime, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!vec || !quat) return fail(RBIS_ERR_INVALID, "vec and quat are required");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (int rc = use_device(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaMemcpyAsync(h->vec, vec, N * 21 * sizeof(double), kind, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->quat, quat, N * 4 * sizeof(double), kind, h->stream));
+  if (cov) {
+    const double* src = cov;
+    if (mem == RBIS_MEM_HOST) {
+      if (h->full_cov.ensure(N * 441)) return fail(RBIS_ERR_ALLOC, "covariance scratch allocation failed");
+      CUDA_TRY(cudaMemcpyAsync(h->full_cov.p, cov, N * 441 * sizeof(double), kind, h->stream));
+      src = h->full_cov.p;
+    }
+    rbisk::pack_cov_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(src, h->P, (long long)N);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  if (loglik) CUDA_TRY(cudaMemcpyAsync(h->loglik, loglik, N * sizeof(double), kind, h->stream));
+  else CUDA_TRY(cudaMemsetAsync(h->loglik, 0, N * sizeof(double), h->stream));
+  if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(h->stream));  // caller may reuse its buffers
+  h->utime = utime;
+  return 0;
+}
+
+int rbis_batch_get_state(rbis_batch_t* h, double* vec, double* quat, double* cov, double* loglik, int64_t* utime,
+                         int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (int rc = use_device(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (vec) CUDA_TRY(cudaMemcpyAsync(vec, h->vec, N * 21 * sizeof(double), kind, h->stream));
+  if (quat) CUDA_TRY(cudaMemcpyAsync(quat, h->quat, N * 4 * sizeof(double), kind, h->stream));
+  if (loglik) CUDA_TRY(cudaMemcpyAsync(loglik, h->loglik, N * sizeof(double), kind, h->stream));
+  if (cov) {
+    double* dst = cov;
+    if (mem == RBIS_MEM_HOST) {
+      if (h->full_cov.ensure(N * 441)) return fail(RBIS_ERR_ALLOC, "covariance scratch allocation failed");
+      dst = h->full_cov.p;
+    }
+    rbisk::unpack_cov_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(h->P, dst, (long long)N);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(cov, dst, N * 441 * sizeof(double), kind, h->stream));
+  }
+  if (utime) *utime = h->utime;
+  if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int rbis_batch_set_filter(rbis_batch_t* h, int64_t n, const double* vec, const double* quat, const double* cov,
+                          double loglik) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (n < 0 || n >= h->N) return fail(RBIS_ERR_INVALID, "filter index out of range");
+  if (int rc = use_device(h)) return rc;
+  const size_t pitch = (size_t)h->N * sizeof(double);
+  if (vec) CUDA_TRY(cudaMemcpy2DAsync(h->vec + n, pitch, vec, sizeof(double), sizeof(double), 21, cudaMemcpyHostToDevice, h->stream));
+  if (quat) CUDA_TRY(cudaMemcpy2DAsync(h->quat + n, pitch, quat, sizeof(double), sizeof(double), 4, cudaMemcpyHostToDevice, h->stream));
+  double packed[rbisk::NP];
+  if (cov) {
+    for (int j = 0; j < 21; j++)
+      for (int i = 0; i <= j; i++) packed[rbisk::slot(i, j)] = cov[i + 21 * j];
+    CUDA_TRY(cudaMemcpy2DAsync(h->P + n, pitch, packed, sizeof(double), sizeof(double), rbisk::NP, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->loglik + n, &loglik, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int rbis_batch_get_filter(rbis_batch_t* h, int64_t n, double* vec, double* quat, double* cov, double* loglik) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (n < 0 || n >= h->N) return fail(RBIS_ERR_INVALID, "filter index out of range");
+  if (int rc = use_device(h)) return rc;
+  const size_t pitch = (size_t)h->N * sizeof(double);
+  double packed[rbisk::NP];
+  if (vec) CUDA_TRY(cudaMemcpy2DAsync(vec, sizeof(double), h->vec + n, pitch, sizeof(double), 21, cudaMemcpyDeviceToHost, h->stream));
+  if (quat) CUDA_TRY(cudaMemcpy2DAsync(quat, sizeof(double), h->quat + n, pitch, sizeof(double), 4, cudaMemcpyDeviceToHost, h->stream));
+  if (cov) CUDA_TRY(cudaMemcpy2DAsync(packed, sizeof(double), h->P + n, pitch, sizeof(double), rbisk::NP, cudaMemcpyDeviceToHost, h->stream));
+  if (loglik) CUDA_TRY(cudaMemcpyAsync(loglik, h->loglik + n, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (cov)
+    for (int j = 0; j < 21; j++)
+      for (int i = 0; i < 21; i++) cov[i + 21 * j] = packed[rbisk::slot(i, j)];
+  return 0;
+}
+
+int rbis_batch_set_process_noise(rbis_batch_t* h, double q_gyro, double q_accel, double q_gyro_bias,
+                                 double q_accel_bias) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (int rc = use_device(h)) return rc;
+  const long long N = h->N;
+  const double q[4] = {q_gyro, q_accel, q_gyro_bias, q_accel_bias};
+  for (int k = 0; k < 4; k++) {
+    rbisk::fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->qparams + k * N, q[k], N);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  return 0;
+}
+
+int rbis_batch_set_process_noise_per_filter(rbis_batch_t* h, const double* q_gyro, const double* q_accel,
+                                            const double* q_gyro_bias, const double* q_accel_bias, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!q_gyro || !q_accel || !q_gyro_bias || !q_accel_bias) return fail(RBIS_ERR_INVALID, "all four arrays are required");
+  if (int rc = use_device(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const double* src[4] = {q_gyro, q_accel, q_gyro_bias, q_accel_bias};
+  for (int k = 0; k < 4; k++) CUDA_TRY(cudaMemcpyAsync(h->qparams + k * N, src[k], N * sizeof(double), kind, h->stream));
+  if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
+                         int n_streams, const rbis_stream_t* streams, int mem) {
+  if (n_streams > 0 && !streams) return fail(RBIS_ERR_INVALID, "streams is NULL");
+  return launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem);
+}
+
+int rbis_batch_ins_step(rbis_batch_t* h, const double* gyro, const double* accel, double dt, int64_t utime, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!gyro || !accel) return fail(RBIS_ERR_INVALID, "gyro and accel are required");
+  if (int rc = use_device(h)) return rc;
+  // assemble one [6][N] IMU row on the device
+  const size_t N = (size_t)h->N;
+  if (h->misc.ensure(6 * N)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaMemcpyAsync(h->misc.p, gyro, 3 * N * sizeof(double), kind, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->misc.p + 3 * N, accel, 3 * N * sizeof(double), kind, h->stream));
+  rbis_op_t op;
+  op.kind = RBIS_OP_IMU; op.stream = 0; op.row = 0; op.utime = utime; op.dt = dt;
+  return launch_fused(h, 1, &op, h->misc.p, 1, 0, nullptr, RBIS_MEM_DEVICE);
+}
+
+static int single_meas(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* quat,
+                       const double* R, int r_mode, int64_t utime, int mem, int has_orient) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (m < 1 || m > RBIS_MAX_MEAS || !idx) return fail(RBIS_ERR_INVALID, "bad m / idx");
+  rbis_stream_t st;
+  std::memset(&st, 0, sizeof(st));
+  st.m = m; st.has_orientation = has_orient; st.r_mode = r_mode;
+  for (int a = 0; a < m; a++) st.idx[a] = idx[a];
+  st.z = z; st.quat = quat; st.R = R; st.rows = 1;
+  rbis_op_t op;
+  op.kind = RBIS_OP_MEAS; op.stream = 0; op.row = 0; op.utime = utime; op.dt = 0;
+  return launch_fused(h, 1, &op, nullptr, 0, 1, &st, mem);
+}
+
+int rbis_batch_indexed_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* R,
+                              int r_mode, int64_t utime, int mem) {
+  return single_meas(h, m, idx, z, nullptr, R, r_mode, utime, mem, 0);
+}
+
+int rbis_batch_indexed_orient_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* quat,
+                                     const double* R, int r_mode, int64_t utime, int mem) {
+  if (!quat) return fail(RBIS_ERR_INVALID, "quat is required");
+  return single_meas(h, m, idx, z, quat, R, r_mode, utime, mem, 1);
+}
+
+int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int per_filter, int chunk,
+                     double* out_chunks, int64_t* n_chunks, double* out_per_filter, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!truth_vec || !truth_quat || !out_chunks) return fail(RBIS_ERR_INVALID, "truth and out_chunks are required");
+  if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
+  if (int rc = use_device(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
+  // scratch: truth (25 or 25N) + per-filter [23][N] + chunks [nch][96]
+  const size_t truth_n = per_filter ? 25 * N : 25;
+  if (h->misc.ensure(truth_n + 23 * N + (size_t)nch * RBIS_NUM_STATS)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  double* d_truth = h->misc.p;
+  double* d_pf = d_truth + truth_n;
+  double* d_chunks = d_pf + 23 * N;
+  const double *tv = d_truth, *tq = d_truth + (per_filter ? 21 * N : 21);
+  if (per_filter && mem == RBIS_MEM_DEVICE) {
+    tv = truth_vec; tq = truth_quat;
+  } else {
+    const size_t nv = per_filter ? 21 * N : 21, nq = per_filter ? 4 * N : 4;
+    CUDA_TRY(cudaMemcpyAsync(d_truth, truth_vec, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_truth + nv, truth_quat, nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  double* pf = d_pf;
+  if (out_per_filter && mem == RBIS_MEM_DEVICE) pf = out_per_filter;
+  rbisk::stats_kernel<<<(unsigned)nch, chunk, chunk * sizeof(double), h->stream>>>(
+      h->vec, h->quat, h->P, h->loglik, tv, tq, per_filter, (long long)N, pf, d_chunks);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out_chunks, d_chunks, (size_t)nch * RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out_per_filter && mem == RBIS_MEM_HOST)
+    CUDA_TRY(cudaMemcpyAsync(out_per_filter, d_pf, 23 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (n_chunks) *n_chunks = nch;
+  return 0;
+}
+
+int rbis_stats_reduce_chunks(const double* chunks, int64_t n_chunks, double* out) {
+  if (!chunks || !out || n_chunks < 0) return fail(RBIS_ERR_INVALID, "bad arguments");
+  for (int k = 0; k < RBIS_NUM_STATS; k++) {
+    double s = 0.0;
+    for (int64_t c = 0; c < n_chunks; c++) s += chunks[c * RBIS_NUM_STATS + k];  // ascending chunk order
+    out[k] = s;
+  }
+  return 0;
+}
+
+int rbis_measure_fp64_peak(int device, int iters, double* dfma_tflops, double* dmma_tflops) {
+  if (iters <= 0) return fail(RBIS_ERR_INVALID, "iters must be positive");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float ms = 0;
+  for (int which = 0; which < 2; which++) {
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {  // first repetition is the warm-up
+      CUDA_TRY(cudaEventRecord(e0));
+      if (which == 0) rbisk::dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0000001);
+      else rbisk::dmma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0000001);
+      CUDA_TRY(cudaEventRecord(e1));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      double flops;
+      if (which == 0) flops = (double)blocks * threads * rbisk::DFMA_CHAINS * 2.0 * iters * rbisk::DFMA_UNROLL;
+      else flops = (double)blocks * (threads / 32) * rbisk::DMMA_CHAINS * rbisk::DMMA_UNROLL * 512.0 * iters;
+      const double tf = flops / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    if (which == 0 && dfma_tflops) *dfma_tflops = best;
+    if (which == 1 && dmma_tflops) *dmma_tflops = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// rbis_stats.cuh -- ensemble statistics (fixed-order chunk reduction) and FP64 peak microbenchmarks.
+//
+// Error definition: SE/noise_id/noise_id.cpp:37-38  (e = est; e.subtractState(truth); e.quatToChi()),
+// NEES over velocity + chi + position (the active set of SE/noise_id/roll_forward.cpp:54-57).
+#pragma once
+#include "rbis_kernels.cuh"
+
+namespace rbisk {
+
+constexpr int NSTAT = 96;
+constexpr int NPF = 23;  // per-filter outputs: e[21], NEES, loglik
+
+// One CTA per chunk of blockDim.x filters.  Each statistic is reduced with the same fixed binary
+// tree (stride blockDim/2 ... 1) so the result depends on nothing but the per-filter values and
+// the chunk size: it is identical for any GPU count and reproducible on the host.
+__global__ void stats_kernel(const double* __restrict__ vec, const double* __restrict__ quat,
+                             const double* __restrict__ P, const double* __restrict__ loglik,
+                             const double* __restrict__ tvec, const double* __restrict__ tquat, int per_filter,
+                             long long N, double* __restrict__ out_pf, double* __restrict__ out_chunks) {
+  extern __shared__ double red[];
+  const int t = threadIdx.x;
+  const long long n = (long long)blockIdx.x * blockDim.x + t;
+  const bool live = n < N;
+  double val[48];
+#pragma unroll
+  for (int k = 0; k < 48; k++) val[k] = 0.0;
+  if (live) {
+    double e[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) e[i] = vec[(long long)i * N + n] - (per_filter ? tvec[(long long)i * N + n] : tvec[i]);
+    const Q4 q{quat[n], quat[N + n], quat[2 * N + n], quat[3 * N + n]};
+    const Q4 tq = per_filter ? Q4{tquat[n], tquat[N + n], tquat[2 * N + n], tquat[3 * N + n]}
+                             : Q4{tquat[0], tquat[1], tquat[2], tquat[3]};
+    const V3 dchi = subtract_quats(q, tq);  // Log(truth^-1 * est)
+    e[6] = dchi.x; e[7] = dchi.y; e[8] = dchi.z;
+    // NEES over indices 3..11: Cholesky of the 9x9 block, forward solve
+    double L[9][9];
+#pragma unroll
+    for (int j = 0; j < 9; j++)
+#pragma unroll
+      for (int i = 0; i <= j; i++) L[j][i] = P[(long long)slot(3 + i, 3 + j) * N + n];  // lower: L[row][col]
+    double y[9];
+    double nees = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      double d = L[j][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+      d = sqrt(d);
+      L[j][j] = d;
+      const double rd = 1.0 / d;
+#pragma unroll
+      for (int i = j + 1; i < 9; i++) {
+        double v = L[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+        L[i][j] = v * rd;
+      }
+      double v = e[3 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= L[j][k] * y[k];
+      y[j] = v * rd;
+      nees += y[j] * y[j];
+    }
+    const double ll = loglik[n];
+    bool finite = isfinite(nees) && isfinite(ll);
+#pragma unroll
+    for (int i = 0; i < NS; i++) finite = finite && isfinite(e[i]);
+    if (out_pf) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) out_pf[(long long)i * N + n] = e[i];
+      out_pf[21LL * N + n] = nees;
+      out_pf[22LL * N + n] = ll;
+    }
+    if (finite) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        val[i] = e[i];
+        val[21 + i] = __dmul_rn(e[i], e[i]);
+      }
+      val[42] = nees;
+      val[43] = __dmul_rn(nees, nees);
+      val[44] = ll;
+      val[47] = (nees >= 2.7003895 && nees <= 19.0227678) ? 1.0 : 0.0;  // chi2(9) 2.5% / 97.5% quantiles
+    } else {
+      val[45] = 1.0;
+    }
+    val[46] = 1.0;
+  }
+  static_for<48>([&](auto k) {
+    red[t] = val[k];
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if (t < s) red[t] = __dadd_rn(red[t], red[t + s]);
+      __syncthreads();
+    }
+    if (t == 0) out_chunks[(long long)blockIdx.x * NSTAT + k] = red[0];
+    __syncthreads();
+  });
+  if (t >= 48 && t < NSTAT) out_chunks[(long long)blockIdx.x * NSTAT + t] = 0.0;
+}
+
+// ---- FP64 roofline denominators ----
+constexpr int DFMA_CHAINS = 8;
+constexpr int DFMA_UNROLL = 32;
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a) {
+  double x[DFMA_CHAINS];
+#pragma unroll
+  for (int c = 0; c < DFMA_CHAINS; c++) x[c] = 1e-3 * threadIdx.x + c;
+  const double b = a * 0.5 - 0.5;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < DFMA_UNROLL; u++)
+#pragma unroll
+      for (int c = 0; c < DFMA_CHAINS; c++) x[c] = fma(x[c], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < DFMA_CHAINS; c++) s += x[c];
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+constexpr int DMMA_CHAINS = 8;
+constexpr int DMMA_UNROLL = 8;
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a) {
+  double c0[DMMA_CHAINS], c1[DMMA_CHAINS];
+#pragma unroll
+  for (int c = 0; c < DMMA_CHAINS; c++) { c0[c] = 1e-3 * threadIdx.x + c; c1[c] = c0[c] + 0.5; }
+  const double av = a * 1e-3, bv = a * 2e-3;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < DMMA_UNROLL; u++)
+#pragma unroll
+      for (int c = 0; c < DMMA_CHAINS; c++)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[c]), "+d"(c1[c])
+                     : "d"(av), "d"(bv));
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < DMMA_CHAINS; c++) s += c0[c] + c1[c];
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace rbisk
