@@ -156,6 +156,35 @@ int rbis_batch_indexed_orient_update(rbis_batch_t* h, int m, const int32_t* idx,
 int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu,
                          int64_t imu_rows, int n_streams, const rbis_stream_t* streams, int mem);
 
+/* ---- delayed measurements: the batch form of MavStateEstimator::addUpdate's out-of-order insert +
+ * replay (MSE/mav_state_est.cpp:28-80) over updateHistory's time-ordered multimap
+ * (MSE/update_history.cpp:16-54), for an ensemble whose filters share one arrival schedule.
+ * The planner keeps the time-ordered list of updates (equal utime keeps arrival order, as the hinted
+ * multimap insert does) and turns arrivals into an op program for rbis_batch_run_fused: in-order
+ * arrivals append ops; an arrival older than the head becomes RESTORE(nearest earlier snapshot) +
+ * the replay of every update from there to the head.  Where the reference keeps a full posterior in
+ * every history node, the device keeps a ring of `snapshot_slots` ensemble snapshots taken every
+ * `snapshot_period_us` (at utimes u with (u - snapshot_phase_us) % period == 0, after the last
+ * update stamped u), plus one at the start.  Updates older than the oldest retained history entry are
+ * discarded as in update_history.cpp:28-39; so are updates that no retained snapshot precedes.
+ * History is truncated to `history_span_us` behind the newest update after every roll-forward
+ * (mav_state_est.cpp:74-77).  Host-side only; no device work. */
+typedef struct rbis_planner rbis_planner_t;
+int rbis_planner_create(rbis_planner_t** out, int64_t utime0, int32_t snapshot_slots, int64_t snapshot_period_us,
+                        int64_t snapshot_phase_us, int64_t history_span_us);
+int rbis_planner_destroy(rbis_planner_t* p);
+/* addUpdate(update, roll_forward): update->kind is RBIS_OP_IMU or RBIS_OP_MEAS.  Returns 0 = accepted,
+ * 1 = discarded (too old), negative = error.  With roll_forward == 0 the update only enters the
+ * history; the next roll-forward processes everything outstanding in one replay. */
+int rbis_planner_add_update(rbis_planner_t* p, const rbis_op_t* update, int roll_forward);
+/* Ops planned so far and not yet taken. */
+int64_t rbis_planner_pending(const rbis_planner_t* p);
+/* Copy out (and clear) the pending program; fails with RBIS_ERR_INVALID if cap is too small. */
+int rbis_planner_take(rbis_planner_t* p, rbis_op_t* out, int64_t cap, int64_t* n_out);
+/* Counters: [0] updates accepted, [1] discarded, [2] rewinds, [3] updates replayed (re-applied),
+ * [4] snapshots taken, [5] history entries retained. */
+int rbis_planner_counters(const rbis_planner_t* p, int64_t out[6]);
+
 /* ---- ensemble statistics against a truth state (error definition of
  * SE/noise_id/noise_id.cpp:37-38; NEES over velocity+chi+position as roll_forward.cpp:54-57).
  * truth_vec [21] / truth_quat [4] (host) shared by all filters, or per-filter [21][N] / [4][N] (`mem`)
@@ -167,6 +196,16 @@ int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, c
  * out_per_filter (optional, `mem`): [23][N] = e[21], NEES, loglik per filter.  Synchronous. */
 int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int per_filter,
                      int chunk, double* out_chunks, int64_t* n_chunks, double* out_per_filter, int mem);
+/* Same reduction, enqueued on the handle's stream without waiting: truth is shared ([21], [4], host),
+ * out_chunks must be PINNED host memory and is valid once a ticket recorded after this call has been
+ * waited for.  Lets a caller read per-chunk results every step without stalling the input copies of
+ * the next step. */
+int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int chunk,
+                             double* out_chunks, int64_t* n_chunks);
+/* Stream-ordered completion tickets: record marks "everything enqueued so far", wait blocks the host
+ * until that point has completed.  Up to 8 tickets may be outstanding. */
+int rbis_batch_record(rbis_batch_t* h, int32_t* ticket);
+int rbis_batch_wait(rbis_batch_t* h, int32_t ticket);
 /* Fixed-order final reduction of chunk partials (ascending chunk index): out[RBIS_NUM_STATS]. */
 int rbis_stats_reduce_chunks(const double* chunks, int64_t n_chunks, double* out);
 

@@ -261,6 +261,24 @@ class RBISBatch:
         return out, pf
 
 
+    def stats_enqueue(self, truth_vec, truth_quat, out_chunks, chunk=1024):
+        """Asynchronous statistics into a PINNED host array [n_chunks][96]; valid after wait(record())."""
+        tv = np.ascontiguousarray(truth_vec, dtype=np.float64); tq = np.ascontiguousarray(truth_quat, dtype=np.float64)
+        assert tv.size == 21 and tq.size == 4
+        n_chunks = (self.N + chunk - 1) // chunk
+        po, _ = _ptr(out_chunks, (n_chunks, capi.NUM_STATS), "out_chunks")
+        nch = C.c_int64(0)
+        capi.check(self.lib.rbis_batch_stats_enqueue(self.h, tv.ctypes.data, tq.ctypes.data, int(chunk), po, C.byref(nch)))
+
+    def record(self):
+        t = C.c_int32(0)
+        capi.check(self.lib.rbis_batch_record(self.h, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        capi.check(self.lib.rbis_batch_wait(self.h, int(ticket)))
+
+
 def reduce_chunks(chunks):
     """Fixed ascending-order sum of chunk partials -> [96] (rbis_stats_reduce_chunks)."""
     chunks = np.ascontiguousarray(chunks, dtype=np.float64)

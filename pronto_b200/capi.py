@@ -80,7 +80,16 @@ PROTOTYPES = {
     "rbis_batch_indexed_update": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "rbis_batch_indexed_orient_update": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "rbis_batch_run_fused": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Op), C.c_void_p, C.c_int64, C.c_int, C.POINTER(Stream), C.c_int]),
+    "rbis_planner_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
+    "rbis_planner_destroy": (C.c_int, [C.c_void_p]),
+    "rbis_planner_add_update": (C.c_int, [C.c_void_p, C.POINTER(Op), C.c_int]),
+    "rbis_planner_pending": (C.c_int64, [C.c_void_p]),
+    "rbis_planner_take": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_int64_p]),
+    "rbis_planner_counters": (C.c_int, [C.c_void_p, c_int64_p]),
     "rbis_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_int64_p, C.c_void_p, C.c_int]),
+    "rbis_batch_stats_enqueue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_int64_p]),
+    "rbis_batch_record": (C.c_int, [C.c_void_p, c_int32_p]),
+    "rbis_batch_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "rbis_stats_reduce_chunks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "rbis_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p]),
 }

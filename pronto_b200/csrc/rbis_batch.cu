@@ -66,6 +66,17 @@ struct StagingSlot {  // device copies of caller-host input arrays for one fused
 
 }  // namespace
 
+// shared with rbis_planner.cpp
+int rbis_set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
 struct rbis_batch {
   int64_t N = 0;
   rbis_batch_config_t cfg{};
@@ -79,11 +90,14 @@ struct rbis_batch {
   std::vector<char> snap_valid;
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
+  DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
   rbisk::Op* d_ops = nullptr;
   size_t d_ops_cap = 0;
   double* d_rshared = nullptr;  // [MAX_STREAMS][81]
   StagingSlot slots[2];
   int slot_toggle = 0;
+  cudaEvent_t tickets[8] = {};
+  int next_ticket = 0;
   int smem_bytes = 0;
 };
 
@@ -329,6 +343,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     CREATE_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
   }
+  for (auto& t : h->tickets) CREATE_TRY(cudaEventCreateWithFlags(&t, cudaEventDisableTiming));
   CREATE_TRY(cudaMalloc(&h->vec, N * 21 * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->quat, N * 4 * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->P, N * rbisk::NP * sizeof(double)));
@@ -361,13 +376,15 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared);
-  h->full_cov.release(); h->misc.release();
+  h->full_cov.release(); h->misc.release(); h->stats_async.release();
   for (auto& s : h->slots) {
     s.imu.release();
     for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
+  for (auto& t : h->tickets)
+    if (t) cudaEventDestroy(t);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaGetLastError();
@@ -583,6 +600,49 @@ int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* tru
     CUDA_TRY(cudaMemcpyAsync(out_per_filter, d_pf, 23 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (n_chunks) *n_chunks = nch;
+  return 0;
+}
+
+int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int chunk,
+                             double* out_chunks, int64_t* n_chunks) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!truth_vec || !truth_quat || !out_chunks) return fail(RBIS_ERR_INVALID, "truth and out_chunks are required");
+  if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
+  if (int rc = use_device(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
+  // separate scratch from rbis_batch_stats so that a pending enqueue is never disturbed by a resize
+  if (h->stats_async.ensure(25 + (size_t)nch * RBIS_NUM_STATS)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  double* d_truth = h->stats_async.p;
+  double* d_chunks = d_truth + 25;
+  double tbuf[25];
+  std::memcpy(tbuf, truth_vec, 21 * sizeof(double));
+  std::memcpy(tbuf + 21, truth_quat, 4 * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(d_truth, tbuf, sizeof(tbuf), cudaMemcpyHostToDevice, h->stream));  // pageable: staged before return
+  rbisk::stats_kernel<<<(unsigned)nch, chunk, chunk * sizeof(double), h->stream>>>(
+      h->vec, h->quat, h->P, h->loglik, d_truth, d_truth + 21, 0, (long long)N, nullptr, d_chunks);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out_chunks, d_chunks, (size_t)nch * RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (n_chunks) *n_chunks = nch;
+  return 0;
+}
+
+int rbis_batch_record(rbis_batch_t* h, int32_t* ticket) {
+  if (!h || !ticket) return fail(RBIS_ERR_INVALID, "null handle or ticket");
+  if (int rc = use_device(h)) return rc;
+  const int t = h->next_ticket;
+  h->next_ticket = (t + 1) % 8;
+  CUDA_TRY(cudaEventRecord(h->tickets[t], h->stream));
+  *ticket = t;
+  return 0;
+}
+
+int rbis_batch_wait(rbis_batch_t* h, int32_t ticket) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (ticket < 0 || ticket >= 8) return fail(RBIS_ERR_INVALID, "bad ticket");
+  if (int rc = use_device(h)) return rc;
+  CUDA_TRY(cudaEventSynchronize(h->tickets[ticket]));
   return 0;
 }
 

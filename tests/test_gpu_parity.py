@@ -1,0 +1,449 @@
+"""Parity of the CUDA path (through the C ABI, librbis_b200.so) against the CPU oracle and the golden
+vectors.  Gates (BASELINE.json north_star / SURVEY.md 8d): <= 1e-9 per step, <= 1e-6 after a 60 s
+1 kHz trajectory, ensemble statistics bit-exact for any sharding.  All tests need a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from pronto_b200 import MeasStream, RBISBatch, capi, reduce_chunks, synth
+from pronto_b200.parity import max_errors
+
+from common import gpu_streams, nominal_q, oracle_streams, random_ensemble, scenario
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rbis_golden.npz")
+STEP_TOL = 1e-9     # per-step gate
+TRAJ_TOL = 1e-6     # after 60 s
+NTHREADS = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def _assert_close(got, ref, tol, what=""):
+    e = max_errors(got[0], got[1], got[2], ref[0], ref[1], ref[2])
+    assert e["vec"] <= tol and e["quat"] <= tol and e["cov"] <= tol, (what, e)
+    return e
+
+
+def _rel_ll(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+# ------------------------------------------------------------------------------------------------
+# single ops
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1, 37, 300])
+def test_ins_step_matches_oracle(oracle, N):
+    vec, quat, cov = random_ensemble(N, seed=N)
+    rng = np.random.default_rng(100 + N)
+    gyro = rng.normal(size=(3, N)) * 0.5
+    accel = rng.normal(size=(3, N)) + np.array([[0], [0], [9.8]])
+    qs = [np.abs(rng.normal(size=N)) * s + s for s in (1e-4, 1e-2, 1e-9, 1e-6)]
+    with RBISBatch(N) as b:
+        b.set_state(vec, quat, cov)
+        b.set_process_noise(*qs)
+        b.ins_step(gyro, accel, 2e-3, utime=2000)
+        gv, gq, gP, gll, ut = b.get_state()
+    assert ut == 2000 and np.all(gll == 0)
+    rv, rq, rP = np.empty_like(vec), np.empty_like(quat), np.empty_like(cov)
+    for n in range(N):
+        rv[:, n], rq[:, n] = oracle.ins_update_state(gyro[:, n], accel[:, n], 2e-3, vec[:, n], quat[:, n])
+        P = oracle.ins_update_covariance(qs[0][n], qs[1][n], qs[2][n], qs[3][n], vec[:, n], quat[:, n],
+                                         cov[:, n].reshape(21, 21).T, 2e-3)
+        rP[:, n] = P.T.reshape(-1)
+    _assert_close((gv, gq, gP), (rv, rq, rP), 1e-12, "ins_step")
+
+
+MEAS_CASES = [
+    ([3, 4, 5], False, "diag"),            # leg-odometry velocity (rbis_legodo_common.cpp:69-73)
+    ([9, 10, 11], False, "diag"),          # pose position (pose_meas.cpp:47,79)
+    ([9, 10, 11, 6, 7, 8], True, "diag"),  # pose fix with orientation (pose_meas.cpp:39-52)
+    ([17], False, "diag"),                 # yaw-bias (rbis_yawlock_update.cpp:79)
+    ([17, 8], True, "diag"),               # yawlock (rbis_yawlock_update.cpp:97-99)
+    ([8, 9, 10, 11], False, "dense"),      # quick-lock (quick_lock.cpp:132), dense R -> general path
+    ([3, 4, 5, 0, 1, 2], False, "diag"),   # vel + angular velocity (rbis_legodo_common.cpp:59-67)
+    ([9, 10, 11, 3, 4, 5, 6, 7, 8], True, "dense"),  # m = 9 (laser_gpf_lib.cpp:108-110)
+    ([9, 10, 11, 8], True, "block"),       # scan match (sensor_handlers.cpp:653-684): 3-block + 1
+    ([6, 7, 8], False, "diag"),            # plain indexed update ON chi indices (z is used)
+]
+
+
+@pytest.mark.parametrize("idx,orient,rkind", MEAS_CASES)
+def test_indexed_update_matches_oracle(oracle, idx, orient, rkind):
+    N, m = 130, len(idx)
+    vec, quat, cov = random_ensemble(N, seed=m * 7 + len(rkind))
+    rng = np.random.default_rng(5 + m)
+    # leave a below-tolerance residual chi in a third of the filters
+    vec[6:9, ::3] = rng.normal(size=(3, len(range(0, N, 3)))) * 2e-7
+    z = np.ascontiguousarray(vec[idx, :] + rng.normal(size=(m, N)) * 0.1)
+    mq = None
+    if orient:
+        d = rng.normal(size=(3, N)) * 0.05
+        n = np.linalg.norm(d, axis=0)
+        dq = np.stack([np.cos(n / 2), *(np.sin(n / 2) * d / n)])
+        w0, x0, y0, z0 = quat
+        w1, x1, y1, z1 = dq
+        mq = np.ascontiguousarray(np.stack([w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
+                                            w0 * y1 + y0 * w1 + z0 * x1 - x0 * z1, w0 * z1 + z0 * w1 + x0 * y1 - y0 * x1]))
+    if rkind == "diag":
+        R = np.diag(np.abs(rng.normal(size=m)) * 0.01 + 0.005)
+    elif rkind == "dense":
+        B = rng.normal(size=(m, m))
+        R = B @ B.T * 0.01 + np.eye(m) * 0.01
+    else:
+        B = rng.normal(size=(3, 3))
+        R = np.zeros((m, m))
+        R[:3, :3] = B @ B.T * 0.01 + np.eye(3) * 0.01
+        R[3, 3] = 0.02
+    with RBISBatch(N) as b:
+        b.set_state(vec, quat, cov, loglik=np.full(N, 1.5))
+        b.indexed_update(idx, z, R, utime=77, quat=mq)
+        gv, gq, gP, gll, ut = b.get_state()
+    assert ut == 77
+    rv, rq, rP, rll = np.empty_like(vec), np.empty_like(quat), np.empty_like(cov), np.empty(N)
+    for n in range(N):
+        pv, pq, pc, ll = oracle.measurement_update(z[:, n], R, idx, vec[:, n], quat[:, n], cov[:, n].reshape(21, 21).T,
+                                                   mq[:, n] if orient else None)
+        rv[:, n], rq[:, n], rP[:, n], rll[n] = pv, pq, pc.T.reshape(-1), 1.5 + ll
+    _assert_close((gv, gq, gP), (rv, rq, rP), 1e-11, f"meas {idx}")
+    assert _rel_ll(gll, rll) < 1e-11
+
+
+def test_per_filter_diagonal_R(oracle):
+    N, idx = 70, [3, 4, 5]
+    vec, quat, cov = random_ensemble(N, seed=9)
+    rng = np.random.default_rng(9)
+    z = np.ascontiguousarray(vec[idx, :] + rng.normal(size=(3, N)) * 0.1)
+    Rd = np.abs(rng.normal(size=(3, N))) * 0.01 + 0.001
+    with RBISBatch(N) as b:
+        b.set_state(vec, quat, cov)
+        b.indexed_update(idx, z, Rd, per_filter_diag=True)
+        gv, gq, gP, gll, _ = b.get_state()
+    for n in range(N):
+        pv, pq, pc, ll = oracle.measurement_update(z[:, n], np.diag(Rd[:, n]), idx, vec[:, n], quat[:, n],
+                                                   cov[:, n].reshape(21, 21).T)
+        assert np.max(np.abs(gv[:, n] - pv)) < 1e-12 and np.max(np.abs(gP[:, n] - pc.T.reshape(-1))) < 1e-13
+        assert abs(gll[n] - ll) < 1e-11 * max(1, abs(ll))
+
+
+def test_single_ops_match_golden(golden):
+    N = 33
+    vec = np.repeat(golden["op_vec"][:, None], N, axis=1)
+    quat = np.repeat(golden["op_quat"][:, None], N, axis=1)
+    cov = np.repeat(golden["op_cov"].T.reshape(-1)[:, None], N, axis=1)
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(vec, quat, cov)
+        b.ins_step(np.repeat(golden["op_gyro"][:, None], N, axis=1), np.repeat(golden["op_accel"][:, None], N, axis=1), 1e-3)
+        gv, gq, gP, _, _ = b.get_state()
+        assert np.max(np.abs(gv - golden["op_ins_vec"][:, None])) < 1e-14
+        assert np.max(np.abs(gq - golden["op_ins_quat"][:, None])) < 1e-14
+        assert np.max(np.abs(gP - golden["op_ins_cov"].T.reshape(-1)[:, None])) < 1e-15
+        for c in range(int(golden["n_meas_cases"])):
+            b.set_state(vec, quat, cov)
+            mq = golden[f"m{c}_mq"]
+            idx = [int(i) for i in golden[f"m{c}_idx"]]
+            b.indexed_update(idx, np.repeat(golden[f"m{c}_z"][:, None], N, axis=1), golden[f"m{c}_R"],
+                             quat=np.repeat(mq[:, None], N, axis=1) if mq.size else None)
+            gv, gq, gP, gll, _ = b.get_state()
+            assert np.max(np.abs(gv - golden[f"m{c}_vec"][:, None])) < 1e-12, c
+            assert np.max(np.abs(gq - golden[f"m{c}_quat"][:, None])) < 1e-12, c
+            assert np.max(np.abs(gP - golden[f"m{c}_cov"].T.reshape(-1)[:, None])) < 1e-13, c
+            assert np.max(np.abs(gll - float(golden[f"m{c}_ll"]))) < 1e-10, c
+            assert np.all(gv == gv[:, :1]) and np.all(gP == gP[:, :1])  # every lane computes the same bits
+
+
+# ------------------------------------------------------------------------------------------------
+# fused programs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["walk", "tumble"])
+def test_fused_trajectory_matches_golden(golden, name):
+    N = 4
+    st = scenario(N, 400)["st"]
+    streams = [MeasStream(synth.LEGODO_IDX, golden[f"{name}_legodo"], st["R_legodo"]),
+               MeasStream(synth.POSE_IDX, golden[f"{name}_pose_z"], st["R_pose"], quat=golden[f"{name}_pose_q"])]
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(golden[f"{name}_in_vec"], golden[f"{name}_in_quat"], golden[f"{name}_in_cov"])
+        b.run_fused(st["events"], imu=golden[f"{name}_imu"], streams=streams)
+        gv, gq, gP, gll, ut = b.get_state()
+    assert ut == st["events"][-1][3]
+    _assert_close((gv, gq, gP), (golden[f"{name}_vec"], golden[f"{name}_quat"], golden[f"{name}_cov"]), STEP_TOL, name)
+    assert _rel_ll(gll, golden[f"{name}_loglik"]) < STEP_TOL
+
+
+@pytest.mark.parametrize("tumbling", [False, True])
+def test_per_step_parity_and_launch_fusion(oracle, tumbling):
+    """Every event applied as its own launch is compared with the oracle's head after the same event
+    (<= 1e-9 per step); the same program in ONE launch must give the same bits."""
+    N, T = 150, 220
+    sc = scenario(N, T, tumbling=tumbling)
+    st = sc["st"]
+    ev = st["events"]
+    ref = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st), ev,
+                              n_threads=NTHREADS, trace=True)
+    worst = dict(vec=0.0, quat=0.0, cov=0.0, ll=0.0)
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        streams = gpu_streams(st)
+        for e, event in enumerate(ev):
+            b.run_fused([event], imu=st["imu"], streams=streams)
+            gv, gq, gP, gll, _ = b.get_state()
+            err = max_errors(gv, gq, gP, ref["trace_vec"][e], ref["trace_quat"][e], ref["trace_cov"][e])
+            err["ll"] = _rel_ll(gll, ref["trace_loglik"][e])
+            for k in worst:
+                worst[k] = max(worst[k], err[k])
+        step_by_step = (gv, gq, gP, gll)
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(ev, imu=st["imu"], streams=streams)
+        fused = b.get_state()
+    assert max(worst.values()) <= STEP_TOL, worst
+    for a, c in zip(step_by_step, fused[:4]):
+        assert np.array_equal(a, c)
+
+
+def test_device_resident_inputs_match_host_inputs():
+    import torch
+
+    N, T = 260, 64
+    sc = scenario(N, T)
+    st = sc["st"]
+    dev = torch.device("cuda:0")
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(st["events"], imu=st["imu"], streams=gpu_streams(st))
+        host = b.get_state()
+        t = {k: torch.from_numpy(st[k]).to(dev) for k in ("imu", "legodo", "pose_z", "pose_q")}
+        b.set_state(torch.from_numpy(sc["vec"]).to(dev), torch.from_numpy(sc["quat"]).to(dev), torch.from_numpy(sc["cov"]).to(dev))
+        torch.cuda.synchronize()
+        b.run_fused(st["events"], imu=t["imu"],
+                    streams=[MeasStream(synth.LEGODO_IDX, t["legodo"], st["R_legodo"]),
+                             MeasStream(synth.POSE_IDX, t["pose_z"], st["R_pose"], quat=t["pose_q"])])
+        dvec = torch.empty(21, N, dtype=torch.float64, device=dev)
+        dcov = torch.empty(441, N, dtype=torch.float64, device=dev)
+        b.get_state_into(vec=dvec, cov=dcov)
+        b.synchronize()
+        assert np.array_equal(dvec.cpu().numpy(), host[0]) and np.array_equal(dcov.cpu().numpy(), host[2])
+
+
+def test_60s_trajectory_config1(oracle):
+    """BASELINE.json config 1 shape (60 s, 1 kHz IMU + 500 Hz leg odometry) plus 10 Hz pose fixes, run
+    in time chunks of 2,000 steps; <= 1e-6 on state and covariance at the end (north_star)."""
+    N, T, CH = 16, 60_000, 2_000
+    truth = synth.truth_trajectory(T)
+    sc0 = scenario(N, 1, truth=truth)
+    vec, quat, cov = sc0["vec"], sc0["quat"], sc0["cov"]
+    rv, rq, rP, rll = vec.copy(), quat.copy(), cov.copy(), np.zeros(N)
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(vec, quat, cov)
+        for k0 in range(0, T, CH):
+            st = synth.make_streams(truth, N, k0, CH)
+            b.run_fused(st["events"], imu=st["imu"], streams=gpu_streams(st))
+            ref = oracle.run_ensemble(rv, rq, rP, rll, k0 * 1000, nominal_q(), st["imu"], oracle_streams(st), st["events"],
+                                      n_threads=NTHREADS)
+            rv, rq, rP, rll = ref["vec"], ref["quat"], ref["cov"], ref["loglik"]
+            b.synchronize()
+        gv, gq, gP, gll, ut = b.get_state()
+    assert ut == T * 1000
+    e = _assert_close((gv, gq, gP), (rv, rq, rP), TRAJ_TOL, "60 s")
+    assert _rel_ll(gll, rll) < TRAJ_TOL
+    print("60 s parity:", e, "loglik", _rel_ll(gll, rll))
+    # the filter tracked the truth
+    tv, tq = synth.truth_state_at(truth, T - 1)
+    assert np.max(np.abs(gv[9:12] - tv[9:12, None])) < 0.5
+
+
+# ------------------------------------------------------------------------------------------------
+# delayed measurements: history rewind (config 5)
+# ------------------------------------------------------------------------------------------------
+def test_delayed_pose_fix_rewind_matches_oracle_history(oracle):
+    """Pose fixes stamped at step k arrive 50 steps late.  Oracle: the reference's multimap insert +
+    replay (mav_state_est.cpp:35-70).  GPU: snapshot at k, restore + update + replay in the op program."""
+    N, T, LAT = 96, 400, 50
+    sc = scenario(N, T)
+    st = sc["st"]
+    ev = st["events"]
+    pose = [e for e in ev if e[0] == 1 and e[1] == 1]
+    arrivals, pending = [], list(pose)
+    for e in ev:
+        if e[0] == 1 and e[1] == 1:
+            continue
+        arrivals.append(e)
+        while pending and e[0] == 0 and e[3] >= pending[0][3] + LAT * 1000:
+            arrivals.append(pending.pop(0))
+    arrivals += pending
+    ref = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st),
+                              arrivals, n_threads=NTHREADS)
+    from pronto_b200.schedule import program_from_arrivals
+
+    n_slots = 3
+    ops, cnt = program_from_arrivals(arrivals, snapshot_slots=n_slots, snapshot_period_us=100_000, snapshot_phase_us=1000)
+    assert cnt["rewinds"] == len(pose) and cnt["discarded"] == 0
+    with RBISBatch(N, snapshot_slots=n_slots) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(ops, imu=st["imu"], streams=gpu_streams(st))
+        gv, gq, gP, gll, _ = b.get_state()
+    _assert_close((gv, gq, gP), (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "rewind")
+    assert _rel_ll(gll, ref["loglik"]) < STEP_TOL
+    n_applied = int(np.sum((ops["kind"] == capi.OP_IMU) | (ops["kind"] == capi.OP_MEAS)))
+    assert n_applied == ref["calls"]  # the device re-applies exactly what the reference's replay re-applies
+
+
+# ------------------------------------------------------------------------------------------------
+# statistics
+# ------------------------------------------------------------------------------------------------
+def test_stats_match_oracle_and_are_sharding_invariant(oracle):
+    N, T, CH = 3000, 40, 256
+    sc = scenario(N, T)
+    st = sc["st"]
+    tv, tq = synth.truth_state_at(sc["truth"], T - 1)
+
+    def run(lo, hi):
+        n = hi - lo
+        sub = lambda a: np.ascontiguousarray(a[..., lo:hi])
+        with RBISBatch(n) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(sub(sc["vec"]), sub(sc["quat"]), sub(sc["cov"]))
+            b.run_fused(st["events"], imu=sub(st["imu"]),
+                        streams=[MeasStream(synth.LEGODO_IDX, sub(st["legodo"]), st["R_legodo"]),
+                                 MeasStream(synth.POSE_IDX, sub(st["pose_z"]), st["R_pose"], quat=sub(st["pose_q"]))])
+            chunks, pf = b.stats(tv, tq, chunk=CH, want_per_filter=True)
+            state = b.get_state()
+        return chunks, pf, state
+
+    chunks, pf, state = run(0, N)
+    assert chunks.shape == ((N + CH - 1) // CH, 96)
+    total = reduce_chunks(chunks)
+    assert total[46] == N and total[45] == 0
+    # per-filter error / NEES against the oracle's definition (noise_id.cpp:37-38)
+    gv, gq, gP = state[0], state[1], state[2]
+    for n in range(0, N, 97):
+        e = oracle.state_error(gv[:, n], gq[:, n], tv, tq)
+        assert np.max(np.abs(pf[:21, n] - e)) < 1e-13
+        P = gP[:, n].reshape(21, 21).T[3:12, 3:12]
+        nees = e[3:12] @ np.linalg.solve(P, e[3:12])
+        assert abs(pf[21, n] - nees) < 1e-9 * max(1.0, nees)
+    assert np.array_equal(pf[22], state[3])
+    assert 4.0 < total[42] / N < 16.0  # mean NEES plausible
+    # host replay of the fixed reduction tree gives the same bits
+    def tree(v):
+        v = np.concatenate([v, np.zeros(CH - len(v))])
+        s = CH // 2
+        while s > 0:
+            v = v[:s] + v[s:2 * s]
+            s //= 2
+        return v[0]
+
+    for c in (0, chunks.shape[0] - 1):
+        sl = slice(c * CH, min(N, (c + 1) * CH))
+        assert tree(pf[3, sl]) == chunks[c, 3]
+        assert tree(pf[21, sl]) == chunks[c, 42]
+        assert tree(pf[5, sl] * pf[5, sl]) == chunks[c, 21 + 5]
+    # shard the ensemble 2 and 4 ways on chunk boundaries: identical chunk partials => identical totals
+    for G in (2, 4):
+        per = ((N + CH - 1) // CH + G - 1) // G * CH
+        parts = [run(g * per, min(N, (g + 1) * per))[0] for g in range(G) if g * per < N]
+        merged = np.concatenate(parts)
+        assert np.array_equal(merged, chunks)
+        assert np.array_equal(reduce_chunks(merged), total)
+
+
+def test_nonfinite_filters_are_counted_not_fatal():
+    N = 64
+    vec, quat, cov = random_ensemble(N, seed=3)
+    vec[4, 10] = np.nan
+    cov[0, 20] = np.inf
+    with RBISBatch(N) as b:
+        b.set_state(vec, quat, cov)
+        b.set_process_noise(*nominal_q())
+        g = np.zeros((3, N)); a = np.zeros((3, N)); a[2] = 9.8
+        b.ins_step(g, a, 1e-3)
+        chunks, _ = b.stats(np.zeros(21), np.array([1.0, 0, 0, 0]), chunk=64)
+    tot = reduce_chunks(chunks)
+    assert tot[46] == N and tot[45] >= 1 and np.isfinite(tot[:45]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# API behaviour
+# ------------------------------------------------------------------------------------------------
+def test_state_roundtrip_and_filter_access():
+    N = 200
+    vec, quat, cov = random_ensemble(N, seed=11)
+    ll = np.arange(N) * 0.5
+    with RBISBatch(N) as b:
+        b.set_state(vec, quat, cov, loglik=ll, utime=123)
+        gv, gq, gP, gll, ut = b.get_state()
+        assert ut == 123 and np.array_equal(gv, vec) and np.array_equal(gq, quat) and np.array_equal(gll, ll)
+        # cov comes back symmetrised from its upper triangle
+        full = cov.reshape(21, 21, N)  # [c][r][N]
+        up = np.where((np.arange(21)[:, None] >= np.arange(21)[None, :])[:, :, None], full, full.transpose(1, 0, 2))
+        assert np.array_equal(gP.reshape(21, 21, N), up)
+        v, q, P, l = b.get_filter(57)
+        assert np.array_equal(v, vec[:, 57]) and np.array_equal(q, quat[:, 57]) and l == ll[57]
+        assert np.array_equal(P, gP[:, 57])
+        b.set_filter(3, v, q, P, 9.0)
+        v3, q3, P3, l3 = b.get_filter(3)
+        assert np.array_equal(v3, v) and np.array_equal(P3, P) and l3 == 9.0
+        assert b.launch_count > 0
+
+
+def test_errors():
+    N = 8
+    with RBISBatch(N, snapshot_slots=2) as b:
+        imu = np.zeros((2, 6, N))
+        with pytest.raises(capi.RBISError, match="out of range"):
+            b.run_fused([(capi.OP_IMU, 0, 5, 0, 1e-3)], imu=imu)
+        with pytest.raises(capi.RBISError, match="dt must be positive"):
+            b.run_fused([(capi.OP_IMU, 0, 0, 0, 0.0)], imu=imu)
+        with pytest.raises(capi.RBISError, match="imu is NULL"):
+            b.run_fused([(capi.OP_IMU, 0, 0, 0, 1e-3)])
+        with pytest.raises(capi.RBISError, match="stream"):
+            b.run_fused([(capi.OP_MEAS, 0, 0, 0, 0.0)])
+        with pytest.raises(capi.RBISError, match="empty snapshot"):
+            b.run_fused([(capi.OP_RESTORE, 0, 1, 0, 0.0)])
+        with pytest.raises(capi.RBISError, match="slot"):
+            b.run_fused([(capi.OP_SNAPSHOT, 0, 2, 0, 0.0)])
+        with pytest.raises(capi.RBISError, match="index"):
+            b.indexed_update([21], np.zeros((1, N)), np.eye(1))
+        with pytest.raises(capi.RBISError):
+            b.indexed_update(list(range(10)), np.zeros((10, N)), np.eye(10))
+        b.run_fused([])  # empty program is a no-op
+        b.run_fused([(capi.OP_SNAPSHOT, 0, 1, 0, 0.0), (capi.OP_RESTORE, 0, 1, 5, 0.0)])
+        assert b.get_state(cov=False)[4] == 5
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size property checks (BASELINE.json sizes; the oracle only sees a slice)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_ensemble_replication_property(oracle):
+    """65,536 filters = 256 distinct filters tiled 256 times: every replica must produce the same bits
+    wherever it sits in the grid, and the distinct 256 must match the oracle."""
+    N, D, T = 65_536, 256, 100
+    sc = scenario(D, T)
+    st = sc["st"]
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (1,) * (a.ndim - 1) + (N // D,)))
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(tile(sc["vec"]), tile(sc["quat"]), tile(sc["cov"]))
+        b.run_fused(st["events"], imu=tile(st["imu"]),
+                    streams=[MeasStream(synth.LEGODO_IDX, tile(st["legodo"]), st["R_legodo"]),
+                             MeasStream(synth.POSE_IDX, tile(st["pose_z"]), st["R_pose"], quat=tile(st["pose_q"]))])
+        gv, gq, gP, gll, _ = b.get_state()
+    for a in (gv, gq, gP, gll[None]):
+        r = a.reshape(a.shape[0], N // D, D)
+        assert np.array_equal(r, np.broadcast_to(r[:, :1], r.shape))
+    ref = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st),
+                              st["events"], n_threads=NTHREADS)
+    _assert_close((gv[:, :D], gq[:, :D], gP[:, :D]), (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "65536")
+    # covariance stays symmetric positive definite on the measured block
+    P = gP[:, 5].reshape(21, 21)
+    assert np.array_equal(P, P.T) and np.all(np.linalg.eigvalsh(P[3:12, 3:12]) > 0)
