@@ -1,0 +1,40 @@
+// One variant of the fused kernel, compiled with -DVNAME=... -DVTAG="..." and tuning -D knobs.
+#include <cuda_runtime.h>
+#include <cstring>
+#include <vector>
+#define rbisk VNAME
+#include "../pronto_b200/csrc/rbis_kernels.cuh"
+struct Variant {
+  const char* name; int tpb; int smem;
+  void (*launch)(void*, int, int, int, cudaStream_t);
+  size_t kparams_size;
+  void (*fill)(void*, long long, double*, double*, double*, double*, double*, const double*, const void*, long long,
+               const double*, const double*, const double*, const double*, const double*);
+  void (*prep)(int);
+};
+std::vector<Variant>& registry();
+namespace {
+void launch(void* blob, int grid, int tpb, int smem, cudaStream_t st) {
+  VNAME::rbis_fused_kernel<<<grid, tpb, smem, st>>>(*(VNAME::KParams*)blob);
+}
+void prep(int smem) { cudaFuncSetAttribute(VNAME::rbis_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+void fill(void* blob, long long N, double* vec, double* quat, double* P, double* ll, double* q4, const double* imu,
+          const void* ops, long long n_ops, const double* z0, const double* z1, const double* q1, const double* R0,
+          const double* R1) {
+  VNAME::KParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.N = N; kp.vec = vec; kp.quat = quat; kp.P = P; kp.loglik = ll;
+  kp.q_gyro = q4; kp.q_accel = q4 + N; kp.q_gyro_bias = q4 + 2 * N; kp.q_accel_bias = q4 + 3 * N;
+  kp.imu = imu; kp.ops = (const VNAME::Op*)ops; kp.n_ops = n_ops; kp.g_val = 9.8; kp.chi_tol = 1e-6; kp.ctor_folds_chi = 1;
+  auto& s0 = kp.streams[0];
+  s0.m = 3; s0.has_orient = 0; s0.r_mode = 0; s0.n_chunks = 1; s0.idx[0] = 3; s0.idx[1] = 4; s0.idx[2] = 5;
+  s0.chunk_start[0] = 0; s0.chunk_len[0] = 3; s0.z = z0; s0.R = R0;
+  auto& s1 = kp.streams[1];
+  s1.m = 6; s1.has_orient = 1; s1.r_mode = 0; s1.n_chunks = 2;
+  int idx[6] = {9, 10, 11, 6, 7, 8};
+  for (int i = 0; i < 6; i++) s1.idx[i] = idx[i];
+  s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; s1.z = z1; s1.quat = q1; s1.R = R1;
+  std::memcpy(blob, &kp, sizeof(kp));
+}
+struct Reg { Reg() { registry().push_back({VTAG, VNAME::TPB, VNAME::SMEM_BYTES, launch, sizeof(VNAME::KParams), fill, prep}); } } reg;
+}  // namespace

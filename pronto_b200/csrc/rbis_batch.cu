@@ -103,7 +103,7 @@ struct rbis_batch {
 
 namespace {
 
-constexpr int kSmemBytes = (rbisk::NP - rbisk::NPW) * rbisk::TPB * (int)sizeof(double);
+constexpr int kSmemBytes = rbisk::SMEM_BYTES;
 
 int use_device(const rbis_batch* h) {
   cudaError_t e = cudaSetDevice(h->cfg.device);

@@ -19,12 +19,23 @@
 #include <cstdint>
 #include <utility>
 
+// Tuning knobs (dev/kbench.cu compiles several settings side by side).
+#ifndef RBIS_FENCE
+#define RBIS_FENCE 1   // 1: compiler memory fences between column groups (bounds load hoisting -> no spills)
+#endif
+#if RBIS_FENCE
+#define RBIS_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define RBIS_SCHED_FENCE() do {} while (0)
+#endif
+
 namespace rbisk {
 
 constexpr int NS = 21;       // rbis_num_states
 constexpr int NP = 231;      // packed upper triangle
 constexpr int NPW = 6;       // slots 0..5 (angular-velocity block) are register resident
 constexpr int TPB = 128;     // filters (= threads) per CTA
+constexpr int SMEM_BYTES = (NP - NPW) * TPB * 8;
 constexpr int MAX_MEAS = 9;
 constexpr int MAX_STREAMS = 8;
 constexpr int MAX_CHUNKS = 9;
@@ -245,7 +256,7 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
   // ---------------- E_p : block row p (9..11), sources v (3..5), chi (6..8) ----------------
   {
     V3 Zv[3], Zc[3], Zp[3];
-    static_for<3>([&](auto k) { Zv[k] = ep_z<3 + k>(P, L); });
+    static_for<3>([&](auto k) { Zv[k] = ep_z<3 + k>(P, L); }); RBIS_SCHED_FENCE();
     static_for<3>([&](auto k) { Zc[k] = ep_z<6 + k>(P, L); });
     static_for<3>([&](auto k) { Zp[k] = ep_z<9 + k>(P, L); });
     // T = Zv + Zc * skew(v);  P'[p,p] = Zp + T (R dt)^T
@@ -266,9 +277,10 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
     static_for<3>([&](auto k) { P.setcol3<9, 3 + k>(Zv[k]); });
     static_for<3>([&](auto k) { P.setcol3<9, 6 + k>(Zc[k]); });
     // remaining columns: omega (0..2), a (12..14), bg (15..17), ba (18..20)
-    static_for<3>([&](auto k) { P.setcol3<9, 0 + k>(ep_z<0 + k>(P, L)); });
-    static_for<9>([&](auto k) { P.setcol3<9, 12 + k>(ep_z<12 + k>(P, L)); });
+    static_for<3>([&](auto k) { P.setcol3<9, 0 + k>(ep_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    static_for<9>([&](auto k) { P.setcol3<9, 12 + k>(ep_z<12 + k>(P, L)); RBIS_SCHED_FENCE(); });
   }
+  RBIS_SCHED_FENCE();
   // ---------------- E_v : block row v (3..5), sources v, chi, bg (15..17), ba (18..20) ----------------
   {
     V3 Zv[3], Zc[3], Zg[3], Za[3];
@@ -299,9 +311,10 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
     static_for<3>([&](auto k) { P.setcol3<3, 15 + k>(Zg[k]); });
     static_for<3>([&](auto k) { P.setcol3<3, 18 + k>(Za[k]); });
     // remaining columns: omega, p (9..11), a (12..14)
-    static_for<3>([&](auto k) { P.setcol3<3, 0 + k>(ev_z<0 + k>(P, L)); });
-    static_for<6>([&](auto k) { P.setcol3<3, 9 + k>(ev_z<9 + k>(P, L)); });
+    static_for<3>([&](auto k) { P.setcol3<3, 0 + k>(ev_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    static_for<6>([&](auto k) { P.setcol3<3, 9 + k>(ev_z<9 + k>(P, L)); RBIS_SCHED_FENCE(); });
   }
+  RBIS_SCHED_FENCE();
   // ---------------- E_chi : block row chi (6..8), sources chi, bg ----------------
   {
     V3 Zc[3], Zg[3], Zv[3];
@@ -325,9 +338,9 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
     P.setcol3<6, 4>({Zv[1].x + qg * (L.v.z), Zv[1].y, Zv[1].z + qg * (-L.v.x)});
     P.setcol3<6, 5>({Zv[2].x + qg * (-L.v.y), Zv[2].y + qg * (L.v.x), Zv[2].z});
     // remaining columns: omega, p, a, ba
-    static_for<3>([&](auto k) { P.setcol3<6, 0 + k>(ec_z<0 + k>(P, L)); });
-    static_for<6>([&](auto k) { P.setcol3<6, 9 + k>(ec_z<9 + k>(P, L)); });
-    static_for<3>([&](auto k) { P.setcol3<6, 18 + k>(ec_z<18 + k>(P, L)); });
+    static_for<3>([&](auto k) { P.setcol3<6, 0 + k>(ec_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    static_for<6>([&](auto k) { P.setcol3<6, 9 + k>(ec_z<9 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    static_for<3>([&](auto k) { P.setcol3<6, 18 + k>(ec_z<18 + k>(P, L)); RBIS_SCHED_FENCE(); });
   }
   // ---------------- rest of Qd and the overwrites, rbis.cpp:116,120-121 ----------------
   {
@@ -504,6 +517,7 @@ __device__ __forceinline__ void meas_chunk(Cov& P, FilterState& s, const StreamD
       for (int a = 0; a < M; a++) acc -= HP[a][i] * g[a];
       P.template set<i, j>(acc);
     });
+    RBIS_SCHED_FENCE();
   });
 
   // residual against the current vec (prior + earlier chunks of this update)
@@ -542,7 +556,7 @@ __device__ __forceinline__ void meas_chunk(Cov& P, FilterState& s, const StreamD
 
 // General chunk (M = 4..9): same mathematics, compact loops, HP in local memory.  Only reached for
 // measurement covariances that are not block diagonal in blocks of <= 3.
-__device__ __forceinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, const StreamDesc& st, int a0,
+__device__ __noinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, const StreamDesc& st, int a0,
                                                 long long row, long long N, long long n, const V3& dquat,
                                                 const V3& chi0) {
   double HP[MAX_MEAS][NS], S[MAX_MEAS][MAX_MEAS], Lm[MAX_MEAS][MAX_MEAS], D[MAX_MEAS], r[MAX_MEAS], y[MAX_MEAS];

@@ -13,7 +13,7 @@ constexpr int NPF = 23;  // per-filter outputs: e[21], NEES, loglik
 // One CTA per chunk of blockDim.x filters.  Each statistic is reduced with the same fixed binary
 // tree (stride blockDim/2 ... 1) so the result depends on nothing but the per-filter values and
 // the chunk size: it is identical for any GPU count and reproducible on the host.
-__global__ void stats_kernel(const double* __restrict__ vec, const double* __restrict__ quat,
+__global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ vec, const double* __restrict__ quat,
                              const double* __restrict__ P, const double* __restrict__ loglik,
                              const double* __restrict__ tvec, const double* __restrict__ tquat, int per_filter,
                              long long N, double* __restrict__ out_pf, double* __restrict__ out_chunks) {
