@@ -3,7 +3,17 @@
 #include <cstring>
 #include <vector>
 #define rbisk VNAME
-#include "../pronto_b200/csrc/rbis_kernels.cuh"
+#ifdef KV1
+#define KFUNC rbis_fused_kernel
+#define SET_FAST(s, c, v)
+#else
+#define KFUNC rbis_fused_kernel<false>
+#define SET_FAST(s, c, v) s.chunk_fast[c] = v
+#endif
+#ifndef KHEADER
+#define KHEADER "../pronto_b200/csrc/rbis_kernels.cuh"
+#endif
+#include KHEADER
 struct Variant {
   const char* name; int tpb; int smem;
   void (*launch)(void*, int, int, int, cudaStream_t);
@@ -15,9 +25,9 @@ struct Variant {
 std::vector<Variant>& registry();
 namespace {
 void launch(void* blob, int grid, int tpb, int smem, cudaStream_t st) {
-  VNAME::rbis_fused_kernel<<<grid, tpb, smem, st>>>(*(VNAME::KParams*)blob);
+  VNAME::KFUNC<<<grid, tpb, smem, st>>>(*(VNAME::KParams*)blob);
 }
-void prep(int smem) { cudaFuncSetAttribute(VNAME::rbis_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
+void prep(int smem) { cudaFuncSetAttribute(VNAME::KFUNC, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
 void fill(void* blob, long long N, double* vec, double* quat, double* P, double* ll, double* q4, const double* imu,
           const void* ops, long long n_ops, const double* z0, const double* z1, const double* q1, const double* R0,
           const double* R1) {
@@ -28,12 +38,12 @@ void fill(void* blob, long long N, double* vec, double* quat, double* P, double*
   kp.imu = imu; kp.ops = (const VNAME::Op*)ops; kp.n_ops = n_ops; kp.g_val = 9.8; kp.chi_tol = 1e-6; kp.ctor_folds_chi = 1;
   auto& s0 = kp.streams[0];
   s0.m = 3; s0.has_orient = 0; s0.r_mode = 0; s0.n_chunks = 1; s0.idx[0] = 3; s0.idx[1] = 4; s0.idx[2] = 5;
-  s0.chunk_start[0] = 0; s0.chunk_len[0] = 3; s0.z = z0; s0.R = R0;
+  s0.chunk_start[0] = 0; s0.chunk_len[0] = 3; SET_FAST(s0, 0, 3); s0.z = z0; s0.R = R0;
   auto& s1 = kp.streams[1];
   s1.m = 6; s1.has_orient = 1; s1.r_mode = 0; s1.n_chunks = 2;
   int idx[6] = {9, 10, 11, 6, 7, 8};
   for (int i = 0; i < 6; i++) s1.idx[i] = idx[i];
-  s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; s1.z = z1; s1.quat = q1; s1.R = R1;
+  s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; SET_FAST(s1, 0, 9); SET_FAST(s1, 1, 6); s1.z = z1; s1.quat = q1; s1.R = R1;
   std::memcpy(blob, &kp, sizeof(kp));
 }
 struct Reg { Reg() { registry().push_back({VTAG, VNAME::TPB, VNAME::SMEM_BYTES, launch, sizeof(VNAME::KParams), fill, prep}); } } reg;

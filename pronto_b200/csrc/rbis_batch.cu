@@ -114,6 +114,16 @@ int use_device(const rbis_batch* h) {
 // Split the m rows of a measurement into consecutive chunks along which R is block diagonal, then
 // merge neighbours greedily up to 3 rows (the register-resident fast path).  Blocks wider than 3
 // stay whole and take the general path.
+// chunk_fast: a 3-row chunk on an aligned index triple (3k, 3k+1, 3k+2) takes the unrolled meas3<I0> path.
+void mark_fast_chunks(rbisk::StreamDesc& d, bool* needs_general) {
+  for (int c = 0; c < d.n_chunks; c++) {
+    const int a0 = d.chunk_start[c];
+    const bool fast = d.chunk_len[c] == 3 && d.idx[a0] % 3 == 0 && d.idx[a0 + 1] == d.idx[a0] + 1 && d.idx[a0 + 2] == d.idx[a0] + 2;
+    d.chunk_fast[c] = fast ? d.idx[a0] : -1;
+    if (!fast) *needs_general = true;
+  }
+}
+
 void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) {
   std::vector<int> cut;  // start indices of finest blocks
   cut.push_back(0);
@@ -225,6 +235,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   }
   std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * 81, 0.0);
   bool any_shared = false;
+  bool needs_general = false;  // some chunk is not an aligned triple -> kernel variant with the general path
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
     rbisk::StreamDesc& d = kp.streams[s];
@@ -239,6 +250,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
     if (in.rows == 0) { d.n_chunks = 0; continue; }
     plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
+    mark_fast_chunks(d, &needs_general);
     if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * N, mem, cst, &d.z)) return rc;
     if (in.has_orientation)
       if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * N, mem, cst, &d.quat)) return rc;
@@ -274,7 +286,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   kp.ops = h->d_ops;
 
   const unsigned grid = (unsigned)((N + rbisk::TPB - 1) / rbisk::TPB);
-  rbisk::rbis_fused_kernel<<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+  if (needs_general) rbisk::rbis_fused_kernel<true><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+  else rbisk::rbis_fused_kernel<false><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
@@ -351,10 +364,11 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   CREATE_TRY(cudaMalloc(&h->qparams, N * 4 * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->d_rshared, (size_t)RBIS_MAX_STREAMS * 81 * sizeof(double)));
   if (c.snapshot_slots > 0) {
-    CREATE_TRY(cudaMalloc(&h->snap, (size_t)c.snapshot_slots * 257 * N * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->snap, (size_t)c.snapshot_slots * rbisk::SNAP_ROWS * N * sizeof(double)));
     h->snap_valid.assign((size_t)c.snapshot_slots, 0);
   }
-  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   // default state: zeros, identity quaternion, zero covariance, zero process noise
   CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
   CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));

@@ -1,18 +1,22 @@
-// rbis_kernels.cuh -- sm_100a FP64 device code of the batched RBIS EKF hot path.
+// rbis_kernels.cuh -- sm_100a FP64 device code of the batched RBIS EKF hot path (v2).
 //
-// Mapping: ONE LANE PER FILTER, 128 filters per CTA, one CTA per SM.  A filter's
-// 21x21 covariance is kept symmetric-packed (231 doubles): 225 of them live in shared memory as
-// Ps[slot][lane] (conflict-free, 225 KB per CTA), the 6 of the angular-velocity block plus the
-// 21+4 state doubles and the log-likelihood live in registers.  State and covariance stay on chip
-// for the whole fused program; per-op inputs (IMU rows, measurement rows) are coalesced
-// structure-of-arrays loads issued at the top of each op and consumed at its end, so their HBM
-// latency hides behind the covariance work of the same op.  No cross-lane communication, no
-// barriers: filters are independent.
+// Mapping: ONE LANE PER FILTER, 256 filters per CTA, one CTA per SM (8 warps, two
+// per scheduler).  A filter's 21x21 covariance is kept symmetric-packed (231 doubles) and stays on
+// chip for the whole fused program, split over two memories that are read concurrently:
+//   * TENSOR MEMORY: the 15x15 "active" part (rows/columns of v, chi, p, b_g, b_a; 120 slots).  Each
+//     thread owns 128 doubles of TMEM (its lane of the warp's 32-lane quarter, 256 32-bit columns)
+//     reached with tcgen05.ld/st.32x32b.x2.  Column fetches are software pipelined: the loads of
+//     column k+1 are in flight while column k is computed; tcgen05.wait::ld sits one column behind.
+//   * SHARED MEMORY: the 111 slots coupled to the angular-velocity / acceleration rows, as
+//     Ps[slot][lane] (conflict free, 222 KB per CTA).
+// State (21+4), log-likelihood and linearisation live in registers.  Per-op inputs (IMU rows,
+// measurement rows) are coalesced structure-of-arrays loads issued at the top of each op and
+// consumed at its end.  No cross-lane communication, no barriers: filters are independent.
 //
 // Reference semantics restated (paths under /root/reference/state-estimator/src/mav_state_est/):
 //   cov_propagate()  = insUpdateCovariance + getIMUProcessLinearizationContinuous  rbis.cpp:12-35,77-122
 //   state_propagate()= insUpdateState                                               rbis.cpp:37-75
-//   meas_chunk<M>()  = matrixMeasurementGetKandCovDelta + indexed[PlusOrientation]Measurement
+//   meas3<I0>() / meas_general() = matrixMeasurementGetKandCovDelta + indexed[PlusOrientation]Measurement
 //                      + the covariance half of rbisApplyDelta                      rbis.cpp:124-227
 //   meas_finish()    = the state half of rbisApplyDelta (addState)                  rbis.cpp:219-227
 #pragma once
@@ -21,32 +25,56 @@
 
 // Tuning knobs (dev/kbench.cu compiles several settings side by side).
 #ifndef RBIS_FENCE
-#define RBIS_FENCE 1   // 1: compiler memory fences between column groups (bounds load hoisting -> no spills)
+#define RBIS_FENCE 1   // 1: compiler memory fences between shared-memory column groups (bounds load hoisting)
 #endif
 #if RBIS_FENCE
 #define RBIS_SCHED_FENCE() asm volatile("" ::: "memory")
 #else
 #define RBIS_SCHED_FENCE() do {} while (0)
 #endif
+#ifndef RBIS_SWEEP_TILE
+#define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
+#endif
 
 namespace rbisk {
 
 constexpr int NS = 21;       // rbis_num_states
 constexpr int NP = 231;      // packed upper triangle
-constexpr int NPW = 6;       // slots 0..5 (angular-velocity block) are register resident
-constexpr int TPB = 128;     // filters (= threads) per CTA
-constexpr int SMEM_BYTES = (NP - NPW) * TPB * 8;
+constexpr int TPB = 256;     // filters (= threads) per CTA
 constexpr int MAX_MEAS = 9;
 constexpr int MAX_STREAMS = 8;
 constexpr int MAX_CHUNKS = 9;
+constexpr int SNAP_ROWS = 257;  // 21 vec + 4 quat + loglik + 231 covariance
 
 __host__ __device__ constexpr int slot(int i, int j) { return i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j; }
+
+// ---- placement of covariance slots ----------------------------------------------------------------
+// active index = row/column of v (3..5), chi (6..8), p (9..11), b_g (15..17), b_a (18..20)
+__host__ __device__ constexpr bool is_act(int k) { return k >= 3 && !(k >= 12 && k < 15); }
+// number of active indices below k
+__host__ __device__ constexpr int nact_below(int k) { return k <= 3 ? 0 : (k <= 12 ? k - 3 : (k <= 15 ? 9 : k - 6)); }
+// (i <= j assumed below)
+__host__ __device__ constexpr bool in_tm(int i, int j) { return is_act(i) && is_act(j); }
+__host__ __device__ constexpr int tm_index(int i, int j) { return nact_below(j) * (nact_below(j) + 1) / 2 + nact_below(i); }
+__host__ __device__ constexpr int tm_before(int i, int j) {
+  return nact_below(j) * (nact_below(j) + 1) / 2 + (is_act(j) ? nact_below(i) : 0);
+}
+__host__ __device__ constexpr int sm_index(int i, int j) { return slot(i, j) - tm_before(i, j); }
+__host__ __device__ constexpr int col_of_slot(int s) { int j = 0; while ((j + 1) * (j + 2) / 2 <= s) j++; return j; }
+__host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s) * (col_of_slot(s) + 1) / 2; }
+
+constexpr int N_TM = 120;   // slots in tensor memory
+constexpr int N_SM = 111;   // slots in shared memory
+static_assert(tm_index(20, 20) == N_TM - 1, "tensor-memory slot count");
+static_assert(sm_index(14, 20) == N_SM - 1, "shared-memory slot count");
+constexpr int SMEM_BYTES = N_SM * TPB * 8;
 
 struct StreamDesc {
   int m, has_orient, r_mode, n_chunks;
   int idx[MAX_MEAS];
   int chunk_start[MAX_CHUNKS];
   int chunk_len[MAX_CHUNKS];
+  int chunk_fast[MAX_CHUNKS];  // >= 0: the chunk is the aligned index triple I0..I0+2 (I0 = chunk_fast) -> meas3<I0>
   const double* z;     // [rows][m][N]
   const double* quat;  // [rows][4][N]
   const double* R;     // r_mode 0: device copy of m*m column-major; 1: [m][N]
@@ -93,63 +121,14 @@ struct V3 {
 __device__ __forceinline__ V3 cross(const V3& a, const V3& b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-
-// Per-lane view of the covariance: compile-time (i,j) accessors resolve to an immediate shared
-// memory offset or to one of the six register-resident slots.
-struct Cov {
-  double* Ps;       // shared base + lane; slot s (>= NPW) at Ps[(s - NPW) * TPB]
-  double pw[NPW];
-  template <int I, int J>
-  __device__ __forceinline__ double get() const {
-    constexpr int s = slot(I, J);
-    if constexpr (s < NPW) return pw[s];
-    else return Ps[(s - NPW) * TPB];
-  }
-  template <int I, int J>
-  __device__ __forceinline__ void set(double v) {
-    constexpr int s = slot(I, J);
-    if constexpr (s < NPW) pw[s] = v;
-    else Ps[(s - NPW) * TPB] = v;
-  }
-  template <int S>
-  __device__ __forceinline__ double gets() const {
-    if constexpr (S < NPW) return pw[S];
-    else return Ps[(S - NPW) * TPB];
-  }
-  template <int S>
-  __device__ __forceinline__ void sets(double v) {
-    if constexpr (S < NPW) pw[S] = v;
-    else Ps[(S - NPW) * TPB] = v;
-  }
-  // runtime slot (slow paths only)
-  __device__ __forceinline__ double getr(int s) const {
-    if (s >= NPW) return Ps[(s - NPW) * TPB];
-    double v = pw[0];
-#pragma unroll
-    for (int k = 1; k < NPW; k++) v = (s == k) ? pw[k] : v;
-    return v;
-  }
-  __device__ __forceinline__ void setr(int s, double v) {
-    if (s >= NPW) { Ps[(s - NPW) * TPB] = v; return; }
-#pragma unroll
-    for (int k = 0; k < NPW; k++) pw[k] = (s == k) ? v : pw[k];
-  }
-  // column C (compile time), runtime row r: element (r, C)
-  template <int C>
-  __device__ __forceinline__ double getrc(int r) const {
-    const int s = (r <= C) ? (C * (C + 1) / 2 + r) : (r * (r + 1) / 2 + C);
-    if constexpr (C * (C + 1) / 2 < NPW) return getr(s);  // only columns 0..2 can hit a register slot
-    else return Ps[(s - NPW) * TPB];
-  }
-  template <int R0, int C>
-  __device__ __forceinline__ V3 col3() const {
-    return {get<R0, C>(), get<R0 + 1, C>(), get<R0 + 2, C>()};
-  }
-  template <int R0, int C>
-  __device__ __forceinline__ void setcol3(const V3& v) {
-    set<R0, C>(v.x); set<R0 + 1, C>(v.y); set<R0 + 2, C>(v.z);
-  }
-};
+// acc + a x b  /  acc - a x b  as two FMAs per component
+__device__ __forceinline__ V3 add_cross(const V3& acc, const V3& a, const V3& b) {
+  return {fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)), fma(a.x, b.y, fma(-a.y, b.x, acc.z))};
+}
+__device__ __forceinline__ V3 sub_cross(const V3& acc, const V3& a, const V3& b) {
+  return {fma(-a.y, b.z, fma(a.z, b.y, acc.x)), fma(-a.z, b.x, fma(a.x, b.z, acc.y)), fma(-a.x, b.y, fma(a.y, b.x, acc.z))};
+}
+__device__ __forceinline__ V3 axpy(double a, const V3& x, const V3& y) { return {fma(a, x.x, y.x), fma(a, x.y, y.y), fma(a, x.z, y.z)}; }
 
 struct FilterState {
   double x[NS];
@@ -199,6 +178,166 @@ __device__ __forceinline__ V3 subtract_quats(const Q4& q1, const Q4& q2) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-memory access.  No "memory" clobbers: the asm statements are volatile, so they keep their
+// program order among themselves, while ordinary shared/global accesses may move around them.
+// Loaded registers become valid only after tm_wait_ld(); consumers are tied to the wait by passing
+// the raw registers through an empty volatile asm placed after it (tm_settle).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tm_ld2(uint32_t taddr, uint32_t& lo, uint32_t& hi) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)));
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
+__device__ __forceinline__ double tm_settle(uint32_t& lo, uint32_t& hi) {
+  asm volatile("" : "+r"(lo), "+r"(hi));
+  return __hiloint2double((int)hi, (int)lo);
+}
+
+// Per-lane view of the covariance.
+struct Cov {
+  double* Ps;    // shared base + lane;  shared slot k at Ps[k * TPB]
+  uint32_t tm;   // tensor-memory address of this thread's first column; slot k at tm + 2k
+  // ---- shared-memory part, compile-time (I, J) ----
+  template <int I, int J>
+  __device__ __forceinline__ double gets() const {
+    constexpr int i = I < J ? I : J, j = I < J ? J : I;
+    static_assert(!in_tm(i, j), "slot lives in tensor memory");
+    return Ps[sm_index(i, j) * TPB];
+  }
+  template <int I, int J>
+  __device__ __forceinline__ void sets(double v) {
+    constexpr int i = I < J ? I : J, j = I < J ? J : I;
+    static_assert(!in_tm(i, j), "slot lives in tensor memory");
+    Ps[sm_index(i, j) * TPB] = v;
+  }
+  template <int R0, int C>
+  __device__ __forceinline__ V3 col3s() const {
+    return {gets<R0, C>(), gets<R0 + 1, C>(), gets<R0 + 2, C>()};
+  }
+  template <int R0, int C>
+  __device__ __forceinline__ void setcol3s(const V3& v) {
+    sets<R0, C>(v.x); sets<R0 + 1, C>(v.y); sets<R0 + 2, C>(v.z);
+  }
+  // ---- either memory, compile-time (I, J): store ----
+  template <int I, int J>
+  __device__ __forceinline__ void set(double v) {
+    constexpr int i = I < J ? I : J, j = I < J ? J : I;
+    if constexpr (in_tm(i, j)) tm_st2(tm + 2 * tm_index(i, j), v);
+    else Ps[sm_index(i, j) * TPB] = v;
+  }
+  template <int R0, int C>
+  __device__ __forceinline__ void setcol3(const V3& v) {
+    set<R0, C>(v.x); set<R0 + 1, C>(v.y); set<R0 + 2, C>(v.z);
+  }
+  // ---- run-time (i, j): slow paths only; blocking ----
+  __device__ __forceinline__ double getr(int i, int j) const {
+    if (i > j) { const int t = i; i = j; j = t; }
+    if (in_tm(i, j)) {
+      uint32_t lo, hi;
+      tm_ld2(tm + 2 * tm_index(i, j), lo, hi);
+      tm_wait_ld();
+      return tm_settle(lo, hi);
+    }
+    return Ps[sm_index(i, j) * TPB];
+  }
+  __device__ __forceinline__ void setr(int i, int j, double v) {
+    if (i > j) { const int t = i; i = j; j = t; }
+    if (in_tm(i, j)) { tm_st2(tm + 2 * tm_index(i, j), v); tm_wait_st(); }
+    else Ps[sm_index(i, j) * TPB] = v;
+  }
+};
+
+// A fetch list L names N covariance elements at compile time: L::N, L::row(k), L::col(k).
+template <int N>
+struct Buf {
+  double d[N];
+  uint32_t lo[N], hi[N];
+};
+template <class L>
+__device__ __forceinline__ void issue(const Cov& P, Buf<L::N>& b) {
+  static_for<L::N>([&](auto kc) {
+    constexpr int k = kc;
+    constexpr int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
+    if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), b.lo[k], b.hi[k]);
+    else b.d[k] = P.Ps[sm_index(i, j) * TPB];
+  });
+}
+template <class L>
+__host__ __device__ constexpr bool any_tm() {
+  bool any = false;
+  for (int k = 0; k < L::N; k++) {
+    const int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
+    any = any || in_tm(i, j);
+  }
+  return any;
+}
+template <class L>
+__device__ __forceinline__ void commit(Buf<L::N>& b) {
+  if constexpr (any_tm<L>()) tm_wait_ld();
+  static_for<L::N>([&](auto kc) {
+    constexpr int k = kc;
+    constexpr int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
+    if constexpr (in_tm(i, j)) b.d[k] = tm_settle(b.lo[k], b.hi[k]);
+  });
+}
+
+// rows R0.., R1.., ... (three each) of column C
+template <int C, int... R0s>
+struct ColRows {
+  static constexpr int N = 3 * (int)sizeof...(R0s);
+  static constexpr int row(int k) {
+    constexpr int r0[] = {R0s...};
+    return r0[k / 3] + k % 3;
+  }
+  static constexpr int col(int) { return C; }
+};
+// packed slots S0 .. S0+N-1
+template <int S0, int N_>
+struct SlotRun {
+  static constexpr int N = N_;
+  static constexpr int row(int k) { return row_of_slot(S0 + k); }
+  static constexpr int col(int k) { return col_of_slot(S0 + k); }
+};
+
+template <int... Cs>
+struct ColList {
+  static constexpr int n = (int)sizeof...(Cs);
+  static constexpr int at(int k) {
+    constexpr int c[] = {Cs...};
+    return c[k];
+  }
+};
+
+template <int K, class A, class B>
+__device__ __forceinline__ auto& pick(A& a, B& b) {
+  if constexpr (K == 0) return a;
+  else return b;
+}
+__device__ __forceinline__ V3 v3at(const double* d, int k) { return {d[3 * k], d[3 * k + 1], d[3 * k + 2]}; }
+
+// Software-pipelined sweep over the compile-time column list Cs...: the fetch of column k+1 is
+// issued before column k is processed by f(column, values).  f may store to the covariance, but
+// never to an element that the fetch of the NEXT column reads (checked per call site, see below).
+template <template <int> class L, class Cols, class F>
+__device__ __forceinline__ void for_columns(const Cov& P, Cols, F&& f) {
+  constexpr int n = Cols::n;
+  constexpr int LN = L<Cols::at(0)>::N;
+  Buf<LN> b0, b1;
+  issue<L<Cols::at(0)>>(P, b0);
+  static_for<n>([&](auto kc) {
+    constexpr int k = kc;
+    auto& cur = pick<k % 2>(b0, b1);
+    auto& nxt = pick<(k + 1) % 2>(b0, b1);
+    commit<L<Cols::at(k)>>(cur);
+    if constexpr (k + 1 < n) issue<L<Cols::at(k + 1 < n ? k + 1 : k)>>(P, nxt);
+    f(std::integral_constant<int, Cols::at(k)>{}, cur.d);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
 // Covariance propagation.  Ad = I + dt*Ac has non-identity block rows v, chi, p only, and because
 // the p-columns of Ac are zero and chi's row has no v-column, Ad factors EXACTLY as
 //     Ad = E_chi * E_v * E_p,   E_X = I + (block row X of dt*Ac),
@@ -206,8 +345,9 @@ __device__ __forceinline__ V3 subtract_quats(const Q4& q1, const Q4& q2) {
 // each touching one block row/column.  For E = I + N (N supported on block row I):
 //     z_c   = P[I,c] + N[I,:] P[:,c]            for every column c
 //     P'[I,c] = z_c (c outside I),   P'[I,I] = Z_I + sum_K Z_K N[I,K]^T
-// Products with the structural zeros/ones of Ad are skipped; everything else is the same
-// arithmetic as the dense product up to summation order.
+// Columns of omega and a (passive: their rows of Ad are identity and nothing reads them back) take
+// all three congruences in ONE pass from the old values.  Products with the structural zeros/ones
+// of Ad are skipped; everything else is the dense product's arithmetic up to summation order.
 // ------------------------------------------------------------------------------------------------
 struct Lin {  // linearisation point quantities, pre-scaled by dt where the reference scales Ac by dt
   V3 v;        // body velocity (unscaled)
@@ -218,140 +358,161 @@ struct Lin {  // linearisation point quantities, pre-scaled by dt where the refe
   double dt;
 };
 
-// (Z * skew(u))[:, j] for Z given as three columns
-__device__ __forceinline__ void mul_skew(const V3 Z[3], const V3& u, V3 out[3]) {
-  out[0] = {u.z * Z[1].x - u.y * Z[2].x, u.z * Z[1].y - u.y * Z[2].y, u.z * Z[1].z - u.y * Z[2].z};
-  out[1] = {u.x * Z[2].x - u.z * Z[0].x, u.x * Z[2].y - u.z * Z[0].y, u.x * Z[2].z - u.z * Z[0].z};
-  out[2] = {u.y * Z[0].x - u.x * Z[1].x, u.y * Z[0].y - u.x * Z[1].y, u.y * Z[0].z - u.x * Z[1].z};
+// rows p:  z = P[p,c] + R dt (P[v,c] - v x P[chi,c])
+__device__ __forceinline__ V3 zp(const Lin& L, const V3& pv, const V3& pc, const V3& pp) {
+  const V3 t = sub_cross(pv, L.v, pc);
+  return {fma(L.Rd[0], t.x, fma(L.Rd[1], t.y, fma(L.Rd[2], t.z, pp.x))), fma(L.Rd[3], t.x, fma(L.Rd[4], t.y, fma(L.Rd[5], t.z, pp.y))),
+          fma(L.Rd[6], t.x, fma(L.Rd[7], t.y, fma(L.Rd[8], t.z, pp.z)))};
+}
+// rows v:  z = P[v,c] - wd x P[v,c] + gd x P[chi,c] - vd x P[bg,c] - dt P[ba,c]
+__device__ __forceinline__ V3 zv(const Lin& L, const V3& pv, const V3& pc, const V3& pg, const V3& pa) {
+  const V3 a = sub_cross(pv, L.wd, pv);
+  const V3 b = add_cross(axpy(-L.dt, pa, {0.0, 0.0, 0.0}), L.gd, pc);  // second chain, joined at the end
+  const V3 c = sub_cross(a, L.vd, pg);
+  return {c.x + b.x, c.y + b.y, c.z + b.z};
+}
+// rows chi:  z = P[chi,c] - wd x P[chi,c] - dt P[bg,c]
+__device__ __forceinline__ V3 zc(const Lin& L, const V3& pc, const V3& pg) { return sub_cross(axpy(-L.dt, pg, pc), L.wd, pc); }
+
+// acc += sign * Z skew(u), Z given as three columns:  (Z skew(u))[:,0] = u.z Z1 - u.y Z2, ...
+template <int SIGN>
+__device__ __forceinline__ void acc_mul_skew(V3 acc[3], const V3 Z[3], const V3& u) {
+  const double ux = SIGN * u.x, uy = SIGN * u.y, uz = SIGN * u.z;
+  acc[0] = axpy(uz, Z[1], axpy(-uy, Z[2], acc[0]));
+  acc[1] = axpy(ux, Z[2], axpy(-uz, Z[0], acc[1]));
+  acc[2] = axpy(uy, Z[0], axpy(-ux, Z[1], acc[2]));
 }
 
-template <int C>
-__device__ __forceinline__ V3 ep_z(const Cov& P, const Lin& L) {
-  // rows p:  z = P[p,c] + R dt (P[v,c] - v x P[chi,c])
-  const V3 pv = P.col3<3, C>(), pc = P.col3<6, C>(), pp = P.col3<9, C>();
-  const V3 k = cross(L.v, pc);
-  const V3 t{pv.x - k.x, pv.y - k.y, pv.z - k.z};
-  return {pp.x + L.Rd[0] * t.x + L.Rd[1] * t.y + L.Rd[2] * t.z, pp.y + L.Rd[3] * t.x + L.Rd[4] * t.y + L.Rd[5] * t.z,
-          pp.z + L.Rd[6] * t.x + L.Rd[7] * t.y + L.Rd[8] * t.z};
-}
-template <int C>
-__device__ __forceinline__ V3 ev_z(const Cov& P, const Lin& L) {
-  // rows v:  z = P[v,c] - wd x P[v,c] + gd x P[chi,c] - vd x P[bg,c] - dt P[ba,c]
-  const V3 pv = P.col3<3, C>(), pc = P.col3<6, C>(), pg = P.col3<15, C>(), pa = P.col3<18, C>();
-  const V3 a = cross(L.wd, pv), b = cross(L.gd, pc), c = cross(L.vd, pg);
-  return {pv.x - a.x + b.x - c.x - L.dt * pa.x, pv.y - a.y + b.y - c.y - L.dt * pa.y,
-          pv.z - a.z + b.z - c.z - L.dt * pa.z};
-}
-template <int C>
-__device__ __forceinline__ V3 ec_z(const Cov& P, const Lin& L) {
-  // rows chi:  z = P[chi,c] - wd x P[chi,c] - dt P[bg,c]
-  const V3 pc = P.col3<6, C>(), pg = P.col3<15, C>();
-  const V3 a = cross(L.wd, pc);
-  return {pc.x - a.x - L.dt * pg.x, pc.y - a.y - L.dt * pg.y, pc.z - a.z - L.dt * pg.z};
-}
+template <int C> using FetchEp = ColRows<C, 3, 6, 9>;        // rows v, chi, p
+template <int C> using FetchEv = ColRows<C, 3, 6, 15, 18>;   // rows v, chi, bg, ba
+template <int C> using FetchEc = ColRows<C, 6, 15>;          // rows chi, bg
+template <int C> using FetchAll = ColRows<C, 3, 6, 9, 15, 18>;
 
-__device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyro, double q_accel,
-                                              double q_gyro_bias, double q_accel_bias) {
+__device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyro, double q_accel, double q_gyro_bias,
+                                              double q_accel_bias) {
   const double dt = L.dt;
-  // ---------------- E_p : block row p (9..11), sources v (3..5), chi (6..8) ----------------
+  const double qg = q_gyro * dt, qa = q_accel * dt;
+  // ---------------- passive columns omega (0..2), a (12..14): one pass, shared memory only ----------------
+  static_for<6>([&](auto kc) {
+    constexpr int c = kc < 3 ? (int)kc : 9 + (int)kc;
+    const V3 pv = P.col3s<3, c>(), pc = P.col3s<6, c>(), pp = P.col3s<9, c>(), pg = P.col3s<15, c>(), pa = P.col3s<18, c>();
+    P.setcol3s<9, c>(zp(L, pv, pc, pp));
+    P.setcol3s<3, c>(zv(L, pv, pc, pg, pa));
+    P.setcol3s<6, c>(zc(L, pc, pg));
+    RBIS_SCHED_FENCE();
+  });
+  // overwrites of rbis.cpp:120-121 (nothing in this step reads these blocks)
+  P.sets<12, 12>(q_accel); P.sets<13, 13>(q_accel); P.sets<14, 14>(q_accel);
+  P.sets<12, 13>(0.0); P.sets<12, 14>(0.0); P.sets<13, 14>(0.0);
+  P.sets<0, 0>(q_gyro); P.sets<1, 1>(q_gyro); P.sets<2, 2>(q_gyro);
+  P.sets<0, 1>(0.0); P.sets<0, 2>(0.0); P.sets<1, 2>(0.0);
+
+  // ---------------- E_p on the active block: block row p (9..11), sources v (3..5), chi (6..8) ----------------
+  // column order p, v, chi, bg, ba.  Stores: (p,v) after the v columns, (p,chi) after the chi columns,
+  // (p,p) after that, (p,c) per column for bg/ba -- none is read by a later fetch of this phase.
   {
-    V3 Zv[3], Zc[3], Zp[3];
-    static_for<3>([&](auto k) { Zv[k] = ep_z<3 + k>(P, L); }); RBIS_SCHED_FENCE();
-    static_for<3>([&](auto k) { Zc[k] = ep_z<6 + k>(P, L); });
-    static_for<3>([&](auto k) { Zp[k] = ep_z<9 + k>(P, L); });
-    // T = Zv + Zc * skew(v);  P'[p,p] = Zp + T (R dt)^T
-    V3 S[3];
-    mul_skew(Zc, L.v, S);
-    V3 T[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) T[k] = {Zv[k].x + S[k].x, Zv[k].y + S[k].y, Zv[k].z + S[k].z};
-    // (T Rd^T)[i][j] = sum_k T[k].i * Rd[3j+k]
-    const double t0[3] = {T[0].x, T[1].x, T[2].x}, t1[3] = {T[0].y, T[1].y, T[2].y}, t2[3] = {T[0].z, T[1].z, T[2].z};
-    auto dotR = [&](const double t[3], int j) { return t[0] * L.Rd[3 * j] + t[1] * L.Rd[3 * j + 1] + t[2] * L.Rd[3 * j + 2]; };
-    P.set<9, 9>(Zp[0].x + dotR(t0, 0));
-    P.set<9, 10>(Zp[1].x + dotR(t0, 1));
-    P.set<9, 11>(Zp[2].x + dotR(t0, 2));
-    P.set<10, 10>(Zp[1].y + dotR(t1, 1));
-    P.set<10, 11>(Zp[2].y + dotR(t1, 2));
-    P.set<11, 11>(Zp[2].z + dotR(t2, 2));
-    static_for<3>([&](auto k) { P.setcol3<9, 3 + k>(Zv[k]); });
-    static_for<3>([&](auto k) { P.setcol3<9, 6 + k>(Zc[k]); });
-    // remaining columns: omega (0..2), a (12..14), bg (15..17), ba (18..20)
-    static_for<3>([&](auto k) { P.setcol3<9, 0 + k>(ep_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
-    static_for<9>([&](auto k) { P.setcol3<9, 12 + k>(ep_z<12 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    V3 Zp[3], T[3], Zb[3];
+    for_columns<FetchEp>(P, ColList<9, 10, 11, 3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20>{}, [&](auto cc, const double* d) {
+      constexpr int c = cc;
+      const V3 z = zp(L, v3at(d, 0), v3at(d, 1), v3at(d, 2));
+      if constexpr (c >= 9 && c < 12) Zp[c - 9] = z;
+      else if constexpr (c >= 3 && c < 6) {
+        T[c - 3] = z;
+        P.setcol3<9, c>(z);
+      } else if constexpr (c >= 6 && c < 9) {
+        Zb[c - 6] = z;
+        P.setcol3<9, c>(z);
+        if constexpr (c == 8) {
+          // T = Zv + Zc skew(v);  P'[p,p] = Zp + T (R dt)^T,  (T Rd^T)[i][j] = sum_k T[k].i * Rd[3j+k]
+          acc_mul_skew<1>(T, Zb, L.v);
+          P.set<9, 9>(fma(T[0].x, L.Rd[0], fma(T[1].x, L.Rd[1], fma(T[2].x, L.Rd[2], Zp[0].x))));
+          P.set<9, 10>(fma(T[0].x, L.Rd[3], fma(T[1].x, L.Rd[4], fma(T[2].x, L.Rd[5], Zp[1].x))));
+          P.set<9, 11>(fma(T[0].x, L.Rd[6], fma(T[1].x, L.Rd[7], fma(T[2].x, L.Rd[8], Zp[2].x))));
+          P.set<10, 10>(fma(T[0].y, L.Rd[3], fma(T[1].y, L.Rd[4], fma(T[2].y, L.Rd[5], Zp[1].y))));
+          P.set<10, 11>(fma(T[0].y, L.Rd[6], fma(T[1].y, L.Rd[7], fma(T[2].y, L.Rd[8], Zp[2].y))));
+          P.set<11, 11>(fma(T[0].z, L.Rd[6], fma(T[1].z, L.Rd[7], fma(T[2].z, L.Rd[8], Zp[2].z))));
+        }
+      } else {
+        P.setcol3<9, c>(z);
+      }
+    });
   }
-  RBIS_SCHED_FENCE();
-  // ---------------- E_v : block row v (3..5), sources v, chi, bg (15..17), ba (18..20) ----------------
+  tm_wait_st();
+  // ---------------- E_v: block row v (3..5), sources v, chi, bg (15..17), ba (18..20) ----------------
+  // column order v, chi, bg, ba, p.  P'[v,v] = Zv + Zv skew(wd) - Zc skew(gd) + Zg skew(vd) - dt Za + Qd[v,v]
+  // is accumulated block by block; each Z block is stored as soon as it is complete.
   {
-    V3 Zv[3], Zc[3], Zg[3], Za[3];
-    static_for<3>([&](auto k) { Zv[k] = ev_z<3 + k>(P, L); });
-    static_for<3>([&](auto k) { Zc[k] = ev_z<6 + k>(P, L); });
-    static_for<3>([&](auto k) { Zg[k] = ev_z<15 + k>(P, L); });
-    static_for<3>([&](auto k) { Za[k] = ev_z<18 + k>(P, L); });
-    // P'[v,v] = Zv + Zv skew(wd) - Zc skew(gd) + Zg skew(vd) - dt Za    (+ Qd[v,v], rbis.cpp:116)
-    V3 A[3], B[3], C[3];
-    mul_skew(Zv, L.wd, A);
-    mul_skew(Zc, L.gd, B);
-    mul_skew(Zg, L.vd, C);
-    V3 N[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      N[k] = {Zv[k].x + A[k].x - B[k].x + C[k].x - dt * Za[k].x, Zv[k].y + A[k].y - B[k].y + C[k].y - dt * Za[k].y,
-              Zv[k].z + A[k].z - B[k].z + C[k].z - dt * Za[k].z};
-    // Qd[v,v] = dt (q_gyro (|v|^2 I - v v^T) + q_accel I)
-    const double vv = L.v.x * L.v.x + L.v.y * L.v.y + L.v.z * L.v.z;
-    const double qg = q_gyro * dt, qa = q_accel * dt;
-    P.set<3, 3>(N[0].x + (qg * (vv - L.v.x * L.v.x) + qa));
-    P.set<3, 4>(N[1].x + (qg * (-L.v.x * L.v.y)));
-    P.set<3, 5>(N[2].x + (qg * (-L.v.x * L.v.z)));
-    P.set<4, 4>(N[1].y + (qg * (vv - L.v.y * L.v.y) + qa));
-    P.set<4, 5>(N[2].y + (qg * (-L.v.y * L.v.z)));
-    P.set<5, 5>(N[2].z + (qg * (vv - L.v.z * L.v.z) + qa));
-    static_for<3>([&](auto k) { P.setcol3<3, 6 + k>(Zc[k]); });
-    static_for<3>([&](auto k) { P.setcol3<3, 15 + k>(Zg[k]); });
-    static_for<3>([&](auto k) { P.setcol3<3, 18 + k>(Za[k]); });
-    // remaining columns: omega, p (9..11), a (12..14)
-    static_for<3>([&](auto k) { P.setcol3<3, 0 + k>(ev_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
-    static_for<6>([&](auto k) { P.setcol3<3, 9 + k>(ev_z<9 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    V3 Nv[3], Zb[3];
+    for_columns<FetchEv>(P, ColList<3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20, 9, 10, 11>{}, [&](auto cc, const double* d) {
+      constexpr int c = cc;
+      const V3 z = zv(L, v3at(d, 0), v3at(d, 1), v3at(d, 2), v3at(d, 3));
+      if constexpr (c >= 9 && c < 12) {
+        P.setcol3<3, c>(z);
+      } else {
+        constexpr int k = c % 3;
+        Zb[k] = z;
+        if constexpr (c >= 18) P.set<c, c>(d[9 + k] + q_accel_bias * dt);  // Qd[ba,ba]; (ba,ba) is not read again in this step
+        if constexpr (k == 2) {
+          if constexpr (c == 5) {
+            Nv[0] = Zb[0]; Nv[1] = Zb[1]; Nv[2] = Zb[2];
+            acc_mul_skew<1>(Nv, Zb, L.wd);
+          } else if constexpr (c == 8) {
+            acc_mul_skew<-1>(Nv, Zb, L.gd);
+            static_for<3>([&](auto kk) { P.setcol3<3, 6 + kk>(Zb[kk]); });
+          } else if constexpr (c == 17) {
+            acc_mul_skew<1>(Nv, Zb, L.vd);
+            static_for<3>([&](auto kk) { P.setcol3<3, 15 + kk>(Zb[kk]); });
+          } else {
+            static_for<3>([&](auto kk) { Nv[kk] = axpy(-dt, Zb[kk], Nv[kk]); });
+            static_for<3>([&](auto kk) { P.setcol3<3, 18 + kk>(Zb[kk]); });
+            // Qd[v,v] = dt (q_gyro (|v|^2 I - v v^T) + q_accel I)      (rbis.cpp:91-116)
+            const double vv = L.v.x * L.v.x + L.v.y * L.v.y + L.v.z * L.v.z;
+            P.set<3, 3>(Nv[0].x + (qg * (vv - L.v.x * L.v.x) + qa));
+            P.set<3, 4>(Nv[1].x + (qg * (-L.v.x * L.v.y)));
+            P.set<3, 5>(Nv[2].x + (qg * (-L.v.x * L.v.z)));
+            P.set<4, 4>(Nv[1].y + (qg * (vv - L.v.y * L.v.y) + qa));
+            P.set<4, 5>(Nv[2].y + (qg * (-L.v.y * L.v.z)));
+            P.set<5, 5>(Nv[2].z + (qg * (vv - L.v.z * L.v.z) + qa));
+          }
+        }
+      }
+    });
   }
-  RBIS_SCHED_FENCE();
-  // ---------------- E_chi : block row chi (6..8), sources chi, bg ----------------
+  tm_wait_st();
+  // ---------------- E_chi: block row chi (6..8), sources chi, bg ----------------
+  // column order chi, bg, v, p, ba.  P'[chi,chi] = Zc + Zc skew(wd) - dt Zg + Qd[chi,chi]
   {
-    V3 Zc[3], Zg[3], Zv[3];
-    static_for<3>([&](auto k) { Zc[k] = ec_z<6 + k>(P, L); });
-    static_for<3>([&](auto k) { Zg[k] = ec_z<15 + k>(P, L); });
-    static_for<3>([&](auto k) { Zv[k] = ec_z<3 + k>(P, L); });  // not a source; done here to fuse Qd[chi,v]
-    V3 A[3];
-    mul_skew(Zc, L.wd, A);
-    const double qg = q_gyro * dt;
-    // P'[chi,chi] = Zc + Zc skew(wd) - dt Zg   (+ Qd[chi,chi] = dt q_gyro I)
-    P.set<6, 6>(Zc[0].x + A[0].x - dt * Zg[0].x + qg);
-    P.set<6, 7>(Zc[1].x + A[1].x - dt * Zg[1].x);
-    P.set<6, 8>(Zc[2].x + A[2].x - dt * Zg[2].x);
-    P.set<7, 7>(Zc[1].y + A[1].y - dt * Zg[1].y + qg);
-    P.set<7, 8>(Zc[2].y + A[2].y - dt * Zg[2].y);
-    P.set<8, 8>(Zc[2].z + A[2].z - dt * Zg[2].z + qg);
-    static_for<3>([&](auto k) { P.setcol3<6, 15 + k>(Zg[k]); });
-    // columns v: P'[chi, v_k] = z + Qd[chi, v_k];  Qd[v,chi] = dt q_gyro skew(v)  =>  Qd[chi_i, v_k] = qg*skew(v)[k][i]
-    // skew(v) = [[0,-vz,vy],[vz,0,-vx],[-vy,vx,0]]
-    P.setcol3<6, 3>({Zv[0].x, Zv[0].y + qg * (-L.v.z), Zv[0].z + qg * (L.v.y)});
-    P.setcol3<6, 4>({Zv[1].x + qg * (L.v.z), Zv[1].y, Zv[1].z + qg * (-L.v.x)});
-    P.setcol3<6, 5>({Zv[2].x + qg * (-L.v.y), Zv[2].y + qg * (L.v.x), Zv[2].z});
-    // remaining columns: omega, p, a, ba
-    static_for<3>([&](auto k) { P.setcol3<6, 0 + k>(ec_z<0 + k>(P, L)); RBIS_SCHED_FENCE(); });
-    static_for<6>([&](auto k) { P.setcol3<6, 9 + k>(ec_z<9 + k>(P, L)); RBIS_SCHED_FENCE(); });
-    static_for<3>([&](auto k) { P.setcol3<6, 18 + k>(ec_z<18 + k>(P, L)); RBIS_SCHED_FENCE(); });
+    V3 Mc[3], Zb[3];
+    for_columns<FetchEc>(P, ColList<6, 7, 8, 15, 16, 17, 3, 4, 5, 9, 10, 11, 18, 19, 20>{}, [&](auto cc, const double* d) {
+      constexpr int c = cc;
+      const V3 z = zc(L, v3at(d, 0), v3at(d, 1));
+      if constexpr (c >= 6 && c < 9) {
+        Zb[c - 6] = z;
+        if constexpr (c == 8) {
+          Mc[0] = Zb[0]; Mc[1] = Zb[1]; Mc[2] = Zb[2];
+          acc_mul_skew<1>(Mc, Zb, L.wd);
+        }
+      } else if constexpr (c >= 15 && c < 18) {
+        constexpr int k = c - 15;
+        Mc[k] = axpy(-dt, z, Mc[k]);
+        P.setcol3<6, c>(z);
+        P.set<c, c>(d[3 + k] + q_gyro_bias * dt);  // Qd[bg,bg]; (bg,bg) is not read again in this step
+        if constexpr (c == 17) {
+          P.set<6, 6>(Mc[0].x + qg); P.set<6, 7>(Mc[1].x); P.set<6, 8>(Mc[2].x);
+          P.set<7, 7>(Mc[1].y + qg); P.set<7, 8>(Mc[2].y);
+          P.set<8, 8>(Mc[2].z + qg);
+        }
+      } else if constexpr (c >= 3 && c < 6) {
+        // P'[chi, v_k] = z + Qd[chi, v_k];  Qd[v,chi] = dt q_gyro skew(v)  =>  Qd[chi_i, v_k] = qg*skew(v)[k][i]
+        if constexpr (c == 3) P.setcol3<6, 3>({z.x, fma(qg, -L.v.z, z.y), fma(qg, L.v.y, z.z)});
+        else if constexpr (c == 4) P.setcol3<6, 4>({fma(qg, L.v.z, z.x), z.y, fma(qg, -L.v.x, z.z)});
+        else P.setcol3<6, 5>({fma(qg, -L.v.y, z.x), fma(qg, L.v.x, z.y), z.z});
+      } else {
+        P.setcol3<6, c>(z);
+      }
+    });
   }
-  // ---------------- rest of Qd and the overwrites, rbis.cpp:116,120-121 ----------------
-  {
-    const double qgb = q_gyro_bias * dt, qab = q_accel_bias * dt;
-    static_for<3>([&](auto k) { P.set<15 + k, 15 + k>(P.get<15 + k, 15 + k>() + qgb); });
-    static_for<3>([&](auto k) { P.set<18 + k, 18 + k>(P.get<18 + k, 18 + k>() + qab); });
-    P.set<12, 12>(q_accel); P.set<13, 13>(q_accel); P.set<14, 14>(q_accel);
-    P.set<12, 13>(0.0); P.set<12, 14>(0.0); P.set<13, 14>(0.0);
-    P.set<0, 0>(q_gyro); P.set<1, 1>(q_gyro); P.set<2, 2>(q_gyro);
-    P.set<0, 1>(0.0); P.set<0, 2>(0.0); P.set<1, 2>(0.0);
-  }
+  tm_wait_st();
 }
 
 // chiToQuat on the filter state: fold vec chi into the quaternion when its norm exceeds the tolerance
@@ -414,162 +575,158 @@ __device__ __forceinline__ double pick_state(const double (&x)[NS], int idx) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One chunk of M (<= 3 fast, <= 9 general) measurement rows a0..a0+M-1 of a stream, processed as a
-// standard EKF update on the CURRENT covariance:  S = R + P[idx,idx];  K^T = S^-1 P[idx,:];
+// Measurement chunks.  A chunk is M consecutive rows a0..a0+M-1 of a stream, processed as a standard
+// EKF update on the CURRENT covariance:  S = R + P[idx,idx];  K^T = S^-1 P[idx,:];
 // P -= P[:,idx] S^-1 P[idx,:];  x += K r;  loglik += -log det S - r^T S^-1 r   (rbis.cpp:134-142).
 // The host splits a stream into chunks only along blocks where R is block diagonal, for which
 // processing the chunks in sequence is algebraically identical to the reference's single batch
 // update (chain rule of the Gaussian likelihood); residuals of later chunks are taken against the
 // already-updated vec, chi residuals against the accumulated chi delta.
+//
+// meas3<I0>: the chunk is the aligned index triple I0, I0+1, I0+2 (leg-odometry velocity 3..5, pose
+// position 9..11, pose orientation 6..8, ...).  With S = L D L^T and Y = L^-1 P[idx,:] the update is
+// P -= Y^T D^-1 Y, x += Y^T D^-1 L^-1 r: only Y (63 doubles) is held in registers, and the 231-slot
+// sweep is software pipelined in tiles over both memories.
 // ------------------------------------------------------------------------------------------------
-template <int M>
-__device__ __forceinline__ void meas_chunk(Cov& P, FilterState& s, const StreamDesc& st, int a0, long long row,
-                                           long long N, long long n, const V3& dquat, const V3& chi0) {
+template <int I0>
+struct HPRow0 {  // elements (I0, c), (I0+1, c), (I0+2, c) for c = 3k..3k+2 -> nine per tile, seven tiles
+  template <int T>
+  struct Tile {
+    static constexpr int N = 9;
+    static constexpr int row(int k) { return I0 + k % 3; }
+    static constexpr int col(int k) { return 3 * T + k / 3; }
+  };
+};
+
+template <int I0>
+__device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& st, int a0, long long row, long long N,
+                                      long long n, const V3& dquat, const V3& chi0) {
   // issue the measurement loads first; they are consumed after the covariance work
-  double z[M], Rd[M];
+  double z[3], Rdg[3];
 #pragma unroll
-  for (int a = 0; a < M; a++) z[a] = __ldg(st.z + (row * st.m + (a0 + a)) * N + n);
+  for (int a = 0; a < 3; a++) z[a] = __ldg(st.z + (row * st.m + (a0 + a)) * N + n);
   if (st.r_mode == 1) {
 #pragma unroll
-    for (int a = 0; a < M; a++) Rd[a] = __ldg(st.R + (long long)(a0 + a) * N + n);
+    for (int a = 0; a < 3; a++) Rdg[a] = __ldg(st.R + (long long)(a0 + a) * N + n);
   }
-  int idx[M];
+  // Y starts as HP = P[idx, :]
+  double Y[3][NS];
+  {
+    Buf<9> b0, b1;
+    issue<typename HPRow0<I0>::template Tile<0>>(P, b0);
+    static_for<7>([&](auto tc) {
+      constexpr int t = tc;
+      auto& cur = pick<t % 2>(b0, b1);
+      auto& nxt = pick<(t + 1) % 2>(b0, b1);
+      commit<typename HPRow0<I0>::template Tile<t>>(cur);
+      if constexpr (t + 1 < 7) issue<typename HPRow0<I0>::template Tile<t + 1>>(P, nxt);
 #pragma unroll
-  for (int a = 0; a < M; a++) idx[a] = st.idx[a0 + a];
-
-  // HP = P[idx, :]
-  double HP[M][NS];
-#pragma unroll
-  for (int a = 0; a < M; a++) static_for<NS>([&](auto c) { HP[a][c] = P.template getrc<c>(idx[a]); });
-
-  // S (symmetric, full storage) = R + P[idx, idx]
-  double S[M][M];
-#pragma unroll
-  for (int a = 0; a < M; a++)
-#pragma unroll
-    for (int b = a; b < M; b++) {
-      const int i = idx[a] < idx[b] ? idx[a] : idx[b], j = idx[a] < idx[b] ? idx[b] : idx[a];
-      double r;
-      if (st.r_mode == 1) r = (a == b) ? Rd[a] : 0.0;
-      else r = __ldg(st.R + (a0 + a) + (long long)st.m * (a0 + b));
-      S[a][b] = r + P.getr(j * (j + 1) / 2 + i);
-      S[b][a] = S[a][b];
-    }
-  // LDL^T (no pivoting; S is SPD), Sinv = L^-T D^-1 L^-1, logdet = sum log d
-  double Lm[M][M], D[M];
-  double logdet = 0;
-#pragma unroll
-  for (int k = 0; k < M; k++) {
-    double d = S[k][k];
-#pragma unroll
-    for (int p = 0; p < k; p++) d -= Lm[k][p] * Lm[k][p] * D[p];
-    D[k] = d;
-    logdet += log(d);
-    const double rd = 1.0 / d;
-#pragma unroll
-    for (int i = k + 1; i < M; i++) {
-      double v = S[i][k];
-#pragma unroll
-      for (int p = 0; p < k; p++) v -= Lm[i][p] * Lm[k][p] * D[p];
-      Lm[i][k] = v * rd;
-    }
-  }
-  // Linv (unit lower): Li[i][j], i > j
-  double Li[M][M];
-#pragma unroll
-  for (int j = 0; j < M; j++) {
-    Li[j][j] = 1.0;
-#pragma unroll
-    for (int i = j + 1; i < M; i++) {
-      double v = -Lm[i][j];
-#pragma unroll
-      for (int k = j + 1; k < i; k++) v -= Lm[i][k] * Li[k][j];
-      Li[i][j] = v;
-    }
-  }
-  double Sinv[M][M];
-#pragma unroll
-  for (int a = 0; a < M; a++)
-#pragma unroll
-    for (int b = a; b < M; b++) {
-      double v = 0;
-#pragma unroll
-      for (int k = b; k < M; k++) v += Li[k][a] * Li[k][b] / D[k];
-      Sinv[a][b] = v;
-      Sinv[b][a] = v;
-    }
-
-  // covariance: for each column j, g_j = Sinv HP[:,j] (= row j of K); P[i,j] -= HP[:,i] . g_j, i <= j
-  static_for<NS>([&](auto jc) {
-    constexpr int j = jc;
-    double g[M];
-#pragma unroll
-    for (int a = 0; a < M; a++) {
-      double v = 0;
-#pragma unroll
-      for (int b = 0; b < M; b++) v += Sinv[a][b] * HP[b][j];
-      g[a] = v;
-    }
-    static_for<j + 1>([&](auto ic) {
-      constexpr int i = ic;
-      double acc = P.template get<i, j>();
-#pragma unroll
-      for (int a = 0; a < M; a++) acc -= HP[a][i] * g[a];
-      P.template set<i, j>(acc);
+      for (int k = 0; k < 9; k++) Y[k % 3][3 * t + k / 3] = cur.d[k];
     });
-    RBIS_SCHED_FENCE();
-  });
-
-  // residual against the current vec (prior + earlier chunks of this update)
-  double r[M];
-#pragma unroll
-  for (int a = 0; a < M; a++) {
-    const int k = idx[a] - 6;
-    if (st.has_orient && k >= 0 && k <= 2) {
-      const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
-      const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
-      r[a] = dq - (pick_state(s.x, idx[a]) - c0);
-    } else {
-      r[a] = z[a] - pick_state(s.x, idx[a]);
-    }
   }
-  double y[M];
-  double quad = 0;
-#pragma unroll
-  for (int a = 0; a < M; a++) {
-    double v = 0;
-#pragma unroll
-    for (int b = 0; b < M; b++) v += Sinv[a][b] * r[b];
-    y[a] = v;
-    quad += r[a] * v;
+  // S (symmetric) = R + P[idx, idx]
+  double S00, S10, S20, S11, S21, S22;
+  if (st.r_mode == 1) {
+    S00 = Rdg[0] + Y[0][I0]; S11 = Rdg[1] + Y[1][I0 + 1]; S22 = Rdg[2] + Y[2][I0 + 2];
+    S10 = Y[1][I0]; S20 = Y[2][I0]; S21 = Y[2][I0 + 1];
+  } else {
+    const double* Rm = st.R + a0 + (long long)st.m * a0;
+    S00 = __ldg(Rm) + Y[0][I0]; S11 = __ldg(Rm + st.m + 1) + Y[1][I0 + 1]; S22 = __ldg(Rm + 2 * st.m + 2) + Y[2][I0 + 2];
+    S10 = __ldg(Rm + 1) + Y[1][I0]; S20 = __ldg(Rm + 2) + Y[2][I0]; S21 = __ldg(Rm + st.m + 2) + Y[2][I0 + 1];
   }
-  // x += K r = HP^T (Sinv r)
+  // LDL^T (no pivoting; S is SPD)
+  const double d0 = S00, r0 = 1.0 / d0;
+  const double l10 = S10 * r0, l20 = S20 * r0;
+  const double d1 = fma(-l10 * l10, d0, S11), r1 = 1.0 / d1;
+  const double l21 = fma(-l20 * l10, d0, S21) * r1;
+  const double d2 = fma(-l21 * l21, d1, fma(-l20 * l20, d0, S22)), r2 = 1.0 / d2;
+  const double logdet = log(d0) + log(d1) + log(d2);
+  // Y = L^-1 HP
 #pragma unroll
   for (int c = 0; c < NS; c++) {
-    double v = 0;
-#pragma unroll
-    for (int a = 0; a < M; a++) v += HP[a][c] * y[a];
-    s.x[c] += v;
+    Y[1][c] = fma(-l10, Y[0][c], Y[1][c]);
+    Y[2][c] = fma(-l21, Y[1][c], fma(-l20, Y[0][c], Y[2][c]));
   }
-  s.ll += -logdet - quad;
+  // covariance sweep: P[i,j] -= sum_a Y[a][i] * (Y[a][j] / d_a), packed order, tiles of RBIS_SWEEP_TILE slots
+  {
+    constexpr int TS = RBIS_SWEEP_TILE;
+    constexpr int NT = (NP + TS - 1) / TS;
+    Buf<TS> b0, b1;
+    issue<SlotRun<0, TS>>(P, b0);
+    static_for<NT>([&](auto tc) {
+      constexpr int t = tc;
+      constexpr int s0 = t * TS;
+      constexpr int len = (NP - s0) < TS ? (NP - s0) : TS;
+      auto& cur = pick<t % 2>(b0, b1);
+      auto& nxt = pick<(t + 1) % 2>(b0, b1);
+      // commit / issue on exactly the slots of the tile
+      if constexpr (any_tm<SlotRun<s0, len>>()) tm_wait_ld();
+      static_for<len>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int i = row_of_slot(s0 + k), j = col_of_slot(s0 + k);
+        if constexpr (in_tm(i, j)) cur.d[k] = tm_settle(cur.lo[k], cur.hi[k]);
+      });
+      if constexpr (t + 1 < NT) {
+        constexpr int s1 = s0 + TS;
+        constexpr int len1 = (NP - s1) < TS ? (NP - s1) : TS;
+        static_for<len1>([&](auto kc) {
+          constexpr int k = kc;
+          constexpr int i = row_of_slot(s1 + k), j = col_of_slot(s1 + k);
+          if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), nxt.lo[k], nxt.hi[k]);
+          else nxt.d[k] = P.Ps[sm_index(i, j) * TPB];
+        });
+      }
+      static_for<len>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int i = row_of_slot(s0 + k), j = col_of_slot(s0 + k);
+        const double v = fma(-Y[0][i], Y[0][j] * r0, fma(-Y[1][i], Y[1][j] * r1, fma(-Y[2][i], Y[2][j] * r2, cur.d[k])));
+        P.template set<i, j>(v);
+      });
+      RBIS_SCHED_FENCE();
+    });
+  }
+  tm_wait_st();
+  // residual against the current vec (prior + earlier chunks of this update)
+  double r[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (I0 == 6 && st.has_orient) {
+      const double dq = (a == 0) ? dquat.x : (a == 1) ? dquat.y : dquat.z;
+      const double c0 = (a == 0) ? chi0.x : (a == 1) ? chi0.y : chi0.z;
+      r[a] = dq - (s.x[I0 + a] - c0);
+    } else {
+      r[a] = z[a] - s.x[I0 + a];
+    }
+  }
+  // e = L^-1 r, u = D^-1 e, x += Y^T u
+  const double e0 = r[0], e1 = fma(-l10, e0, r[1]), e2 = fma(-l21, e1, fma(-l20, e0, r[2]));
+  const double u0 = e0 * r0, u1 = e1 * r1, u2 = e2 * r2;
+#pragma unroll
+  for (int c = 0; c < NS; c++) s.x[c] += fma(Y[0][c], u0, fma(Y[1][c], u1, Y[2][c] * u2));
+  s.ll += -logdet - (e0 * u0 + e1 * u1 + e2 * u2);
 }
 
-// General chunk (M = 4..9): same mathematics, compact loops, HP in local memory.  Only reached for
-// measurement covariances that are not block diagonal in blocks of <= 3.
-__device__ __noinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, const StreamDesc& st, int a0,
-                                                long long row, long long N, long long n, const V3& dquat,
-                                                const V3& chi0) {
+// General chunk (any M <= 9, any indices): same mathematics, compact loops, run-time element access,
+// HP in local memory.  Correctness path for index sets that are not aligned triples.
+struct GenResult {
+  double dx[NS];
+  double dll;
+};
+__device__ __noinline__ GenResult meas_general(int M, Cov P, const double* __restrict__ xs, int has_orient, int r_mode,
+                                               int m_stream, const int* __restrict__ idxs, const double* __restrict__ zrow,
+                                               const double* __restrict__ Rp, int a0, long long N, long long n, V3 dquat,
+                                               V3 chi0) {
   double HP[MAX_MEAS][NS], S[MAX_MEAS][MAX_MEAS], Lm[MAX_MEAS][MAX_MEAS], D[MAX_MEAS], r[MAX_MEAS], y[MAX_MEAS];
   int idx[MAX_MEAS];
-  for (int a = 0; a < M; a++) idx[a] = st.idx[a0 + a];
+  for (int a = 0; a < M; a++) idx[a] = idxs[a0 + a];
   for (int a = 0; a < M; a++)
-    for (int c = 0; c < NS; c++) HP[a][c] = P.getr(slot(idx[a], c));
+    for (int c = 0; c < NS; c++) HP[a][c] = P.getr(idx[a], c);
   for (int a = 0; a < M; a++)
     for (int b = 0; b < M; b++) {
       double rr;
-      if (st.r_mode == 1) rr = (a == b) ? __ldg(st.R + (long long)(a0 + a) * N + n) : 0.0;
-      else rr = __ldg(st.R + (a0 + a) + (long long)st.m * (a0 + b));
-      S[a][b] = rr + P.getr(slot(idx[a], idx[b]));
+      if (r_mode == 1) rr = (a == b) ? __ldg(Rp + (long long)(a0 + a) * N + n) : 0.0;
+      else rr = __ldg(Rp + (a0 + a) + (long long)m_stream * (a0 + b));
+      S[a][b] = rr + HP[a][idx[b]];
     }
   double logdet = 0;
   for (int k = 0; k < M; k++) {
@@ -583,7 +740,7 @@ __device__ __noinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, c
       Lm[i][k] = v / d;
     }
   }
-  // G = S^-1 HP by forward / diagonal / backward substitution, column by column (in place in W)
+  // G = S^-1 HP by forward / diagonal / backward substitution, column by column
   double G[MAX_MEAS][NS];
   for (int c = 0; c < NS; c++) {
     double w[MAX_MEAS];
@@ -602,20 +759,19 @@ __device__ __noinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, c
   }
   for (int j = 0; j < NS; j++)
     for (int i = 0; i <= j; i++) {
-      const int sl = j * (j + 1) / 2 + i;
-      double acc = P.getr(sl);
+      double acc = P.getr(i, j);
       for (int a = 0; a < M; a++) acc -= HP[a][i] * G[a][j];
-      P.setr(sl, acc);
+      P.setr(i, j, acc);
     }
   for (int a = 0; a < M; a++) {
     const int k = idx[a] - 6;
-    const double xi = pick_state(s.x, idx[a]);
-    if (st.has_orient && k >= 0 && k <= 2) {
+    const double xi = xs[idx[a]];
+    if (has_orient && k >= 0 && k <= 2) {
       const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
       const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
       r[a] = dq - (xi - c0);
     } else {
-      r[a] = __ldg(st.z + (row * st.m + (a0 + a)) * N + n) - xi;
+      r[a] = __ldg(zrow + (long long)(a0 + a) * N + n) - xi;
     }
   }
   // y = S^-1 r
@@ -632,13 +788,14 @@ __device__ __noinline__ void meas_chunk_general(int M, Cov& P, FilterState& s, c
   }
   double quad = 0;
   for (int a = 0; a < M; a++) quad += r[a] * y[a];
-#pragma unroll
+  GenResult out;
   for (int c = 0; c < NS; c++) {
     double v = 0;
     for (int a = 0; a < M; a++) v += HP[a][c] * y[a];
-    s.x[c] += v;
+    out.dx[c] = v;
   }
-  s.ll += -logdet - quad;
+  out.dll = -logdet - quad;
+  return out;
 }
 
 // state half of rbisApplyDelta for a whole measurement op: dstate = RBIS(K r) then addState.
@@ -654,12 +811,48 @@ __device__ __forceinline__ void meas_finish(FilterState& s, const V3& chi0, doub
   add_state_tail(s, dchi, folded, dq, chi_tol, renorm);
 }
 
+// ---- whole-covariance transfers between the on-chip layout and a [231][stride] global array ----
+constexpr int XFER_TILE = 11;  // 231 = 21 * 11
+__device__ __forceinline__ void cov_load_all(Cov& P, const double* __restrict__ src, long long stride) {
+  static_for<NP>([&](auto sc) {
+    constexpr int s_ = sc;
+    P.template set<row_of_slot(s_), col_of_slot(s_)>(src[(long long)s_ * stride]);
+  });
+  tm_wait_st();
+}
+__device__ __forceinline__ void cov_store_all(const Cov& P, double* __restrict__ dst, long long stride, bool active) {
+  static_for<NP / XFER_TILE>([&](auto tc) {
+    constexpr int s0 = tc * XFER_TILE;
+    Buf<XFER_TILE> b;
+    issue<SlotRun<s0, XFER_TILE>>(P, b);
+    commit<SlotRun<s0, XFER_TILE>>(b);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < XFER_TILE; k++) dst[(long long)(s0 + k) * stride] = b.d[k];
+    }
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused kernel: every lane loads its filter, runs the whole op program, stores it back.
+// GENERAL = false is launched when every measurement chunk of every stream is an aligned triple.
 // ------------------------------------------------------------------------------------------------
+template <bool GENERAL>
 __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constant__ KParams p) {
   extern __shared__ double smem[];
+  __shared__ uint32_t tm_base_s;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  // ---- tensor memory: all 512 columns; warp w owns lanes 32*(w%4).. and columns 256*(w/4).. ----
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm_base = tm_base_s;
+
   const long long N = p.N;
   long long n = (long long)blockIdx.x * TPB + tid;
   const bool active = n < N;
@@ -667,13 +860,12 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
 
   Cov P;
   P.Ps = smem + tid;
+  P.tm = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
   FilterState s;
   static_for<NS>([&](auto i) { s.x[i] = p.vec[(long long)i * N + n]; });
   s.qw = p.quat[n]; s.qx = p.quat[N + n]; s.qy = p.quat[2 * N + n]; s.qz = p.quat[3 * N + n];
   s.ll = p.loglik[n];
-  static_for<NP>([&](auto e) { P.template sets<e>(p.P[(long long)e * N + n]); });
-  const double q_gyro = p.q_gyro[n], q_accel = p.q_accel[n], q_gyro_bias = p.q_gyro_bias[n],
-               q_accel_bias = p.q_accel_bias[n];
+  cov_load_all(P, p.P + n, N);
 
   for (long long oi = 0; oi < p.n_ops; oi++) {
     const Op op = p.ops[oi];
@@ -682,6 +874,8 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
       const double* base = p.imu + op.row * 6 * N + n;
       const V3 gyro{__ldg(base), __ldg(base + N), __ldg(base + 2 * N)};
       const V3 acc{__ldg(base + 3 * N), __ldg(base + 4 * N), __ldg(base + 5 * N)};
+      const double q_gyro = __ldg(p.q_gyro + n), q_accel = __ldg(p.q_accel + n), q_gyro_bias = __ldg(p.q_gyro_bias + n),
+                   q_accel_bias = __ldg(p.q_accel_bias + n);
       const double dt = op.dt;
       const Q4 q{s.qw, s.qx, s.qy, s.qz};
       const V3 gb = qrot(qinv(q), V3{0.0, 0.0, -p.g_val});
@@ -714,30 +908,46 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
       const V3 chi0{s.x[6], s.x[7], s.x[8]};
       for (int ci = 0; ci < st.n_chunks; ci++) {
         const int a0 = st.chunk_start[ci];
-        switch (st.chunk_len[ci]) {
-          case 1: meas_chunk<1>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 2: meas_chunk<2>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 3: meas_chunk<3>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          default: meas_chunk_general(st.chunk_len[ci], P, s, st, a0, op.row, N, n, dquat, chi0); break;
+        const int fast = st.chunk_fast[ci];
+        switch (fast) {
+          case 0: meas3<0>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 3: meas3<3>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 6: meas3<6>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 9: meas3<9>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 12: meas3<12>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 15: meas3<15>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 18: meas3<18>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          default:
+            if constexpr (GENERAL) {
+              double xs[NS];
+#pragma unroll
+              for (int c = 0; c < NS; c++) xs[c] = s.x[c];
+              const GenResult g = meas_general(st.chunk_len[ci], P, xs, st.has_orient, st.r_mode, st.m, st.idx,
+                                               st.z + op.row * st.m * N, st.R, a0, N, n, dquat, chi0);
+#pragma unroll
+              for (int c = 0; c < NS; c++) s.x[c] += g.dx[c];
+              s.ll += g.dll;
+            }
+            break;
         }
       }
       meas_finish(s, chi0, p.chi_tol, p.ctor_folds_chi, p.renorm);
     } else if (op.kind == 2) {
       // ---- snapshot into ring slot ----
+      double* d = p.snap + op.row * SNAP_ROWS * N + n;
       if (active) {
-        double* d = p.snap + op.row * 257 * N + n;
         static_for<NS>([&](auto i) { d[(long long)i * N] = s.x[i]; });
         d[21 * N] = s.qw; d[22 * N] = s.qx; d[23 * N] = s.qy; d[24 * N] = s.qz;
         d[25 * N] = s.ll;
-        static_for<NP>([&](auto e) { d[(long long)(26 + e) * N] = P.template gets<e>(); });
       }
+      cov_store_all(P, d + 26 * N, N, active);
     } else {
       // ---- restore from ring slot ----
-      const double* d = p.snap + op.row * 257 * N + n;
+      const double* d = p.snap + op.row * SNAP_ROWS * N + n;
       static_for<NS>([&](auto i) { s.x[i] = d[(long long)i * N]; });
       s.qw = d[21 * N]; s.qx = d[22 * N]; s.qy = d[23 * N]; s.qz = d[24 * N];
       s.ll = d[25 * N];
-      static_for<NP>([&](auto e) { P.template sets<e>(d[(long long)(26 + e) * N]); });
+      cov_load_all(P, d + 26 * N, N);
     }
   }
 
@@ -745,8 +955,12 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
     static_for<NS>([&](auto i) { p.vec[(long long)i * N + n] = s.x[i]; });
     p.quat[n] = s.qw; p.quat[N + n] = s.qx; p.quat[2 * N + n] = s.qy; p.quat[3 * N + n] = s.qz;
     p.loglik[n] = s.ll;
-    static_for<NP>([&](auto e) { p.P[(long long)e * N + n] = P.template gets<e>(); });
   }
+  cov_store_all(P, p.P + n, N, active);
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
