@@ -80,6 +80,26 @@ __global__ void __launch_bounds__(256, 1) tmem_probe(int mode, int iters, double
       if (v != 1000.0 * threadIdx.x + k + 0.5 * blockIdx.x) bad++;
     }
     if (bad) atomicAdd(errors, bad);
+  } else if (mode == 1) {
+    // scoreboard check: consume tcgen05.ld results WITHOUT tcgen05.wait::ld, values change every round
+    int bad = 0;
+    for (int it = 0; it < iters; it++) {
+      for (int k = 0; k < 128; k++) tm_st2(my + 2 * k, 1000.0 * threadIdx.x + k + 0.25 * it);
+      tm_wait_st();
+      double sum = 0, expect = 0;
+#pragma unroll
+      for (int k = 0; k < 128; k += 8) {
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) tm_ld2(my + 2 * (k + j), lo[j], hi[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum = fma(__hiloint2double((int)hi[j], (int)lo[j]), 1.0 + j, sum);
+#pragma unroll
+        for (int j = 0; j < 8; j++) expect = fma(1000.0 * threadIdx.x + (k + j) + 0.25 * it, 1.0 + j, expect);
+      }
+      if (sum != expect) bad++;
+    }
+    if (bad) atomicAdd(errors, bad);
   } else if (mode == 5) {
     if (warp == 0) {
       t0 = clock64();
@@ -125,12 +145,12 @@ int main() {
   const int smem = 100 * 256 * 8;
   CK(cudaFuncSetAttribute(tmem_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  struct M { int mode; const char* name; } modes[] = {{0, "correctness"}, {5, "LDTM latency (ld+wait, 1 warp)"},
+  struct M { int mode; const char* name; } modes[] = {{0, "correctness"}, {1, "no-wait"}, {5, "LDTM latency (ld+wait, 1 warp)"},
     {10, "32 LDS"}, {11, "32 LDTM"}, {12, "32 STTM"}, {13, "32 LDS + 16 LDTM"}, {14, "32 LDS + 32 LDTM"}, {15, "64 DFMA"},
     {16, "64 DFMA + 16 LDS"}, {17, "64 DFMA + 16 LDTM"}, {18, "64 DFMA + 16 LDS + 8 LDTM + 8 STTM"}, {19, "64 DFMA + 32 LDS"},
     {20, "64 DFMA + 24 LDS + 12 LDTM + 8 STTM"}};
   for (auto& m : modes) {
-    const int iters = m.mode == 0 ? 1 : 4000;
+    const int iters = m.mode == 0 ? 1 : (m.mode == 1 ? 300 : 4000);
     CK(cudaMemset(cyc, 0, 148 * 8 * 8));
     CK(cudaEventRecord(e0));
     tmem_probe<<<148, 256, smem>>>(m.mode, iters, out, cyc, err);
@@ -139,6 +159,7 @@ int main() {
     long long h[8]; CK(cudaMemcpy(h, cyc, 64, cudaMemcpyDeviceToHost));
     int herr; CK(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
     if (m.mode == 0) { printf("tmem correctness: errors=%d\n", herr); continue; }
+    if (m.mode == 1) { printf("tmem loads consumed without wait::ld (scoreboard only), 300 rounds x 128 slots x 8 warps x 148 SMs: errors=%d\n", herr); continue; }
     if (m.mode == 5) { printf("tmem ld+wait dependent latency: %.1f cycles\n", (double)h[0] / iters / 16); continue; }
     printf("mix %-40s: %7.1f cycles per iteration of 8 warps/SM (all 8 warps do the mix)\n", m.name, (double)h[0] / iters);
   }

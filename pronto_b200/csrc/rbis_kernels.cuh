@@ -3,12 +3,13 @@
 // Mapping: ONE LANE PER FILTER, 256 filters per CTA, one CTA per SM (8 warps, two
 // per scheduler).  A filter's 21x21 covariance is kept symmetric-packed (231 doubles) and stays on
 // chip for the whole fused program, split over two memories that are read concurrently:
-//   * TENSOR MEMORY: the 15x15 "active" part (rows/columns of v, chi, p, b_g, b_a; 120 slots).  Each
-//     thread owns 128 doubles of TMEM (its lane of the warp's 32-lane quarter, 256 32-bit columns)
-//     reached with tcgen05.ld/st.32x32b.x2.  Column fetches are software pipelined: the loads of
-//     column k+1 are in flight while column k is computed; tcgen05.wait::ld sits one column behind.
-//   * SHARED MEMORY: the 111 slots coupled to the angular-velocity / acceleration rows, as
-//     Ps[slot][lane] (conflict free, 222 KB per CTA).
+//   * SHARED MEMORY: 113 slots as Ps[slot][lane] (conflict free, 226 KB per CTA) -- the 15x15 "active"
+//     part (rows/columns of v, chi, p, b_g, b_a), which is touched 5.5 times per slot and step;
+//   * TENSOR MEMORY: the other 118 slots (everything coupled to the angular-velocity / acceleration
+//     rows, touched 2-3 times per step, plus the (b_a,b_a) block).  Each thread owns 128 doubles of
+//     TMEM (its lane of the warp's 32-lane quarter, 256 32-bit columns) reached with
+//     tcgen05.ld/st.32x32b.x2; fetches are software pipelined (loads of column k+1 in flight while
+//     column k is computed).  RBIS_PLACEMENT=0 swaps the two roles.
 // State (21+4), log-likelihood and linearisation live in registers.  Per-op inputs (IMU rows,
 // measurement rows) are coalesced structure-of-arrays loads issued at the top of each op and
 // consumed at its end.  No cross-lane communication, no barriers: filters are independent.
@@ -32,6 +33,15 @@
 #else
 #define RBIS_SCHED_FENCE() do {} while (0)
 #endif
+#ifndef RBIS_TM_WAIT_LD
+#define RBIS_TM_WAIT_LD 1  // 1: tcgen05.wait::ld before the loaded registers are read (PTX rule); 0: rely on the scoreboard
+#endif
+#ifndef RBIS_TM_PACK
+#define RBIS_TM_PACK 1  // 1: the b32 pair of a tensor-memory load is packed into its double inside the load's asm block
+#endif
+#ifndef RBIS_STAGE_FENCE
+#define RBIS_STAGE_FENCE 0  // 1: compiler memory fence after every column stage (bounds shared-memory load hoisting)
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -51,22 +61,52 @@ __host__ __device__ constexpr int slot(int i, int j) { return i <= j ? j * (j + 
 // ---- placement of covariance slots ----------------------------------------------------------------
 // active index = row/column of v (3..5), chi (6..8), p (9..11), b_g (15..17), b_a (18..20)
 __host__ __device__ constexpr bool is_act(int k) { return k >= 3 && !(k >= 12 && k < 15); }
-// number of active indices below k
-__host__ __device__ constexpr int nact_below(int k) { return k <= 3 ? 0 : (k <= 12 ? k - 3 : (k <= 15 ? 9 : k - 6)); }
-// (i <= j assumed below)
-__host__ __device__ constexpr bool in_tm(int i, int j) { return is_act(i) && is_act(j); }
-__host__ __device__ constexpr int tm_index(int i, int j) { return nact_below(j) * (nact_below(j) + 1) / 2 + nact_below(i); }
-__host__ __device__ constexpr int tm_before(int i, int j) {
-  return nact_below(j) * (nact_below(j) + 1) / 2 + (is_act(j) ? nact_below(i) : 0);
-}
-__host__ __device__ constexpr int sm_index(int i, int j) { return slot(i, j) - tm_before(i, j); }
 __host__ __device__ constexpr int col_of_slot(int s) { int j = 0; while ((j + 1) * (j + 2) / 2 <= s) j++; return j; }
 __host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s) * (col_of_slot(s) + 1) / 2; }
+#ifndef RBIS_PLACEMENT
+#define RBIS_PLACEMENT 1
+#endif
+// Which memory holds slot (i <= j):
+//   placement 0: the 15x15 active part in tensor memory, the omega/a-coupled part in shared memory;
+//   placement 1: the reverse -- the active part (5.5 accesses per slot and step, most values used by several
+//                FMAs) in shared memory, whose loads land in any register, and the passive part (2-3 accesses)
+//                in tensor memory; 113 slots fit in shared memory, so the (b_a,b_a) block and (17,17) stay in TMEM.
+__host__ __device__ constexpr bool slot_in_tm(int i, int j) {
+#if RBIS_PLACEMENT == 0
+  return is_act(i) && is_act(j);
+#else
+  return !(is_act(i) && is_act(j)) || i >= 18 || (i == 17 && j == 17);
+#endif
+}
+struct Placement {
+  short idx[NP];  // index within its memory
+  bool tm[NP];
+  int n_tm, n_sm;
+};
+constexpr Placement make_placement() {
+  Placement pl{};
+  int nt = 0, ns = 0;
+  for (int j = 0; j < NS; j++)
+    for (int i = 0; i <= j; i++) {
+      const int s_ = slot(i, j);
+      pl.tm[s_] = slot_in_tm(i, j);
+      pl.idx[s_] = (short)(pl.tm[s_] ? nt++ : ns++);
+    }
+  pl.n_tm = nt;
+  pl.n_sm = ns;
+  return pl;
+}
+constexpr Placement kPlace = make_placement();
+__constant__ Placement c_place = make_placement();  // run-time copy for the general (slow) path
+// (i <= j assumed below)
+__host__ __device__ constexpr bool in_tm(int i, int j) { return kPlace.tm[slot(i, j)]; }
+__host__ __device__ constexpr int tm_index(int i, int j) { return kPlace.idx[slot(i, j)]; }
+__host__ __device__ constexpr int sm_index(int i, int j) { return kPlace.idx[slot(i, j)]; }
 
-constexpr int N_TM = 120;   // slots in tensor memory
-constexpr int N_SM = 111;   // slots in shared memory
-static_assert(tm_index(20, 20) == N_TM - 1, "tensor-memory slot count");
-static_assert(sm_index(14, 20) == N_SM - 1, "shared-memory slot count");
+constexpr int N_TM = kPlace.n_tm;   // slots in tensor memory
+constexpr int N_SM = kPlace.n_sm;   // slots in shared memory
+static_assert(N_TM <= 128, "a thread owns 128 doubles of tensor memory");
+static_assert(N_SM * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
 constexpr int SMEM_BYTES = N_SM * TPB * 8;
 
 struct StreamDesc {
@@ -189,38 +229,38 @@ __device__ __forceinline__ void tm_ld2(uint32_t taddr, uint32_t& lo, uint32_t& h
 __device__ __forceinline__ void tm_st2(uint32_t taddr, double v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)));
 }
-__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;"); }
+__device__ __forceinline__ void tm_wait_ld() {
+#if RBIS_TM_WAIT_LD
+  asm volatile("tcgen05.wait::ld.sync.aligned;");
+#endif
+}
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
 __device__ __forceinline__ double tm_settle(uint32_t& lo, uint32_t& hi) {
   asm volatile("" : "+r"(lo), "+r"(hi));
   return __hiloint2double((int)hi, (int)lo);
+}
+// Same load with the register pair packed into a double inside the asm block.  The pack is a pure
+// register rename for ptxas (it tracks tcgen05.ld results with the scoreboard and schedules their
+// consumers itself); keeping the pair and the double in one block lets it coalesce them, where separate
+// b32 outputs cost two MOVs per loaded value.  tm_settle_d pins consumers behind tm_wait_ld().
+__device__ __forceinline__ void tm_ldd(uint32_t taddr, double& d) {
+  asm volatile("{\n\t.reg .b32 lo, hi;\n\ttcgen05.ld.sync.aligned.32x32b.x2.b32 {lo, hi}, [%1];\n\tmov.b64 %0, {lo, hi};\n\t}" : "=d"(d) : "r"(taddr));
+}
+#ifndef RBIS_TM_SETTLE
+#define RBIS_TM_SETTLE 0  // 1: pin every consumer behind the wait with a volatile no-op (serialises the column stages)
+#endif
+__device__ __forceinline__ void tm_settle_d(double& d) {
+#if RBIS_TM_SETTLE
+  asm volatile("" : "+d"(d));
+#else
+  (void)d;
+#endif
 }
 
 // Per-lane view of the covariance.
 struct Cov {
   double* Ps;    // shared base + lane;  shared slot k at Ps[k * TPB]
   uint32_t tm;   // tensor-memory address of this thread's first column; slot k at tm + 2k
-  // ---- shared-memory part, compile-time (I, J) ----
-  template <int I, int J>
-  __device__ __forceinline__ double gets() const {
-    constexpr int i = I < J ? I : J, j = I < J ? J : I;
-    static_assert(!in_tm(i, j), "slot lives in tensor memory");
-    return Ps[sm_index(i, j) * TPB];
-  }
-  template <int I, int J>
-  __device__ __forceinline__ void sets(double v) {
-    constexpr int i = I < J ? I : J, j = I < J ? J : I;
-    static_assert(!in_tm(i, j), "slot lives in tensor memory");
-    Ps[sm_index(i, j) * TPB] = v;
-  }
-  template <int R0, int C>
-  __device__ __forceinline__ V3 col3s() const {
-    return {gets<R0, C>(), gets<R0 + 1, C>(), gets<R0 + 2, C>()};
-  }
-  template <int R0, int C>
-  __device__ __forceinline__ void setcol3s(const V3& v) {
-    sets<R0, C>(v.x); sets<R0 + 1, C>(v.y); sets<R0 + 2, C>(v.z);
-  }
   // ---- either memory, compile-time (I, J): store ----
   template <int I, int J>
   __device__ __forceinline__ void set(double v) {
@@ -234,19 +274,21 @@ struct Cov {
   }
   // ---- run-time (i, j): slow paths only; blocking ----
   __device__ __forceinline__ double getr(int i, int j) const {
-    if (i > j) { const int t = i; i = j; j = t; }
-    if (in_tm(i, j)) {
+    const int s_ = slot(i, j);
+    const int k = c_place.idx[s_];
+    if (c_place.tm[s_]) {
       uint32_t lo, hi;
-      tm_ld2(tm + 2 * tm_index(i, j), lo, hi);
+      tm_ld2(tm + 2 * k, lo, hi);
       tm_wait_ld();
       return tm_settle(lo, hi);
     }
-    return Ps[sm_index(i, j) * TPB];
+    return Ps[k * TPB];
   }
   __device__ __forceinline__ void setr(int i, int j, double v) {
-    if (i > j) { const int t = i; i = j; j = t; }
-    if (in_tm(i, j)) { tm_st2(tm + 2 * tm_index(i, j), v); tm_wait_st(); }
-    else Ps[sm_index(i, j) * TPB] = v;
+    const int s_ = slot(i, j);
+    const int k = c_place.idx[s_];
+    if (c_place.tm[s_]) { tm_st2(tm + 2 * k, v); tm_wait_st(); }
+    else Ps[k * TPB] = v;
   }
 };
 
@@ -261,7 +303,11 @@ __device__ __forceinline__ void issue(const Cov& P, Buf<L::N>& b) {
   static_for<L::N>([&](auto kc) {
     constexpr int k = kc;
     constexpr int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
+#if RBIS_TM_PACK
+    if constexpr (in_tm(i, j)) tm_ldd(P.tm + 2 * tm_index(i, j), b.d[k]);
+#else
     if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), b.lo[k], b.hi[k]);
+#endif
     else b.d[k] = P.Ps[sm_index(i, j) * TPB];
   });
 }
@@ -280,7 +326,11 @@ __device__ __forceinline__ void commit(Buf<L::N>& b) {
   static_for<L::N>([&](auto kc) {
     constexpr int k = kc;
     constexpr int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
+#if RBIS_TM_PACK
+    if constexpr (in_tm(i, j)) tm_settle_d(b.d[k]);
+#else
     if constexpr (in_tm(i, j)) b.d[k] = tm_settle(b.lo[k], b.hi[k]);
+#endif
   });
 }
 
@@ -333,7 +383,10 @@ __device__ __forceinline__ void for_columns(const Cov& P, Cols, F&& f) {
     auto& nxt = pick<(k + 1) % 2>(b0, b1);
     commit<L<Cols::at(k)>>(cur);
     if constexpr (k + 1 < n) issue<L<Cols::at(k + 1 < n ? k + 1 : k)>>(P, nxt);
-    f(std::integral_constant<int, Cols::at(k)>{}, cur.d);
+    f(std::integral_constant<int, Cols::at(k)>{}, cur.d, kc);
+#if RBIS_STAGE_FENCE
+    RBIS_SCHED_FENCE();
+#endif
   });
 }
 
@@ -391,28 +444,21 @@ template <int C> using FetchAll = ColRows<C, 3, 6, 9, 15, 18>;
 __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyro, double q_accel, double q_gyro_bias,
                                               double q_accel_bias) {
   const double dt = L.dt;
-  const double qg = q_gyro * dt, qa = q_accel * dt;
-  // ---------------- passive columns omega (0..2), a (12..14): one pass, shared memory only ----------------
-  static_for<6>([&](auto kc) {
-    constexpr int c = kc < 3 ? (int)kc : 9 + (int)kc;
-    const V3 pv = P.col3s<3, c>(), pc = P.col3s<6, c>(), pp = P.col3s<9, c>(), pg = P.col3s<15, c>(), pa = P.col3s<18, c>();
-    P.setcol3s<9, c>(zp(L, pv, pc, pp));
-    P.setcol3s<3, c>(zv(L, pv, pc, pg, pa));
-    P.setcol3s<6, c>(zc(L, pc, pg));
+  // ---------------- passive columns omega (0..2), a (12..14): all three congruences in one pass ----------------
+  for_columns<FetchAll>(P, ColList<0, 1, 2, 12, 13, 14>{}, [&](auto cc, const double* d, auto) {
+    constexpr int c = cc;
+    const V3 pv = v3at(d, 0), pc = v3at(d, 1), pp = v3at(d, 2), pg = v3at(d, 3), pa = v3at(d, 4);
+    P.setcol3<9, c>(zp(L, pv, pc, pp));
+    P.setcol3<3, c>(zv(L, pv, pc, pg, pa));
+    P.setcol3<6, c>(zc(L, pc, pg));
     RBIS_SCHED_FENCE();
   });
-  // overwrites of rbis.cpp:120-121 (nothing in this step reads these blocks)
-  P.sets<12, 12>(q_accel); P.sets<13, 13>(q_accel); P.sets<14, 14>(q_accel);
-  P.sets<12, 13>(0.0); P.sets<12, 14>(0.0); P.sets<13, 14>(0.0);
-  P.sets<0, 0>(q_gyro); P.sets<1, 1>(q_gyro); P.sets<2, 2>(q_gyro);
-  P.sets<0, 1>(0.0); P.sets<0, 2>(0.0); P.sets<1, 2>(0.0);
-
   // ---------------- E_p on the active block: block row p (9..11), sources v (3..5), chi (6..8) ----------------
   // column order p, v, chi, bg, ba.  Stores: (p,v) after the v columns, (p,chi) after the chi columns,
   // (p,p) after that, (p,c) per column for bg/ba -- none is read by a later fetch of this phase.
   {
     V3 Zp[3], T[3], Zb[3];
-    for_columns<FetchEp>(P, ColList<9, 10, 11, 3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20>{}, [&](auto cc, const double* d) {
+    for_columns<FetchEp>(P, ColList<9, 10, 11, 3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20>{}, [&](auto cc, const double* d, auto stage) {
       constexpr int c = cc;
       const V3 z = zp(L, v3at(d, 0), v3at(d, 1), v3at(d, 2));
       if constexpr (c >= 9 && c < 12) Zp[c - 9] = z;
@@ -441,9 +487,10 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
   // ---------------- E_v: block row v (3..5), sources v, chi, bg (15..17), ba (18..20) ----------------
   // column order v, chi, bg, ba, p.  P'[v,v] = Zv + Zv skew(wd) - Zc skew(gd) + Zg skew(vd) - dt Za + Qd[v,v]
   // is accumulated block by block; each Z block is stored as soon as it is complete.
+  const double qg = q_gyro * dt, qa = q_accel * dt;
   {
     V3 Nv[3], Zb[3];
-    for_columns<FetchEv>(P, ColList<3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20, 9, 10, 11>{}, [&](auto cc, const double* d) {
+    for_columns<FetchEv>(P, ColList<3, 4, 5, 6, 7, 8, 15, 16, 17, 18, 19, 20, 9, 10, 11>{}, [&](auto cc, const double* d, auto stage) {
       constexpr int c = cc;
       const V3 z = zv(L, v3at(d, 0), v3at(d, 1), v3at(d, 2), v3at(d, 3));
       if constexpr (c >= 9 && c < 12) {
@@ -483,7 +530,7 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
   // column order chi, bg, v, p, ba.  P'[chi,chi] = Zc + Zc skew(wd) - dt Zg + Qd[chi,chi]
   {
     V3 Mc[3], Zb[3];
-    for_columns<FetchEc>(P, ColList<6, 7, 8, 15, 16, 17, 3, 4, 5, 9, 10, 11, 18, 19, 20>{}, [&](auto cc, const double* d) {
+    for_columns<FetchEc>(P, ColList<6, 7, 8, 15, 16, 17, 3, 4, 5, 9, 10, 11, 18, 19, 20>{}, [&](auto cc, const double* d, auto stage) {
       constexpr int c = cc;
       const V3 z = zc(L, v3at(d, 0), v3at(d, 1));
       if constexpr (c >= 6 && c < 9) {
@@ -512,6 +559,12 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
       }
     });
   }
+  tm_wait_st();
+  // overwrites of rbis.cpp:120-121 (nothing in this step reads these blocks)
+  P.set<12, 12>(q_accel); P.set<13, 13>(q_accel); P.set<14, 14>(q_accel);
+  P.set<12, 13>(0.0); P.set<12, 14>(0.0); P.set<13, 14>(0.0);
+  P.set<0, 0>(q_gyro); P.set<1, 1>(q_gyro); P.set<2, 2>(q_gyro);
+  P.set<0, 1>(0.0); P.set<0, 2>(0.0); P.set<1, 2>(0.0);
   tm_wait_st();
 }
 
@@ -664,7 +717,11 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
       static_for<len>([&](auto kc) {
         constexpr int k = kc;
         constexpr int i = row_of_slot(s0 + k), j = col_of_slot(s0 + k);
+#if RBIS_TM_PACK
+        if constexpr (in_tm(i, j)) tm_settle_d(cur.d[k]);
+#else
         if constexpr (in_tm(i, j)) cur.d[k] = tm_settle(cur.lo[k], cur.hi[k]);
+#endif
       });
       if constexpr (t + 1 < NT) {
         constexpr int s1 = s0 + TS;
@@ -672,7 +729,11 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
         static_for<len1>([&](auto kc) {
           constexpr int k = kc;
           constexpr int i = row_of_slot(s1 + k), j = col_of_slot(s1 + k);
+#if RBIS_TM_PACK
+          if constexpr (in_tm(i, j)) tm_ldd(P.tm + 2 * tm_index(i, j), nxt.d[k]);
+#else
           if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), nxt.lo[k], nxt.hi[k]);
+#endif
           else nxt.d[k] = P.Ps[sm_index(i, j) * TPB];
         });
       }
@@ -867,8 +928,10 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   s.ll = p.loglik[n];
   cov_load_all(P, p.P + n, N);
 
+  Op op_next = p.ops[0];
   for (long long oi = 0; oi < p.n_ops; oi++) {
-    const Op op = p.ops[oi];
+    const Op op = op_next;
+    if (oi + 1 < p.n_ops) op_next = p.ops[oi + 1];  // fetched one op ahead: its latency hides behind this op
     if (op.kind == 0) {
       // ---- IMU process step ----
       const double* base = p.imu + op.row * 6 * N + n;
