@@ -38,6 +38,12 @@ F_PROP = 4 * 21 ** 3 + 21 ** 2                     # 37,485  
 F_UPD = lambda m: 882 * m + 42 * m * m + 441 + 42 * m
 BYTES_PER_STEP = 48 + 24 / 2 + (48 + 32) / 100     # IMU + leg odometry + pose rows actually read (z has 6 columns)
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+# FP64 instructions the fused kernel EXECUTES per filter-step on this workload, from the ncu instruction mix
+# committed under profiles/ (r1_ncu_full_v2*_instmix.csv: warp-level DFMA / DMUL / DADD per warp-step)
+EXECUTED = {"dfma": 1640.78, "dmul": 149.64, "dadd": 143.33, "source": "profiles/r1_ncu_full_v2d_bench_instmix.csv"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch of this workload (65,536 filters x 200 steps), from the
+# ncu --set full capture of `bench.py --steps 3 --warmup 3` summarised in profiles/r1_ncu_full_v2d_bench_summary.csv
+NCU_TRAFFIC = {"filters": 65_536, "chunk_steps": 200, "bytes": 942.650880e6 + 88.238592e6}
 
 
 def log(*a):
@@ -295,8 +301,10 @@ def run_b200(args):
         b.synchronize()
 
     # ---- warm-up ----
+    tv, tq = synth.truth_state_at(truth, n_chunks_run * Tc - 1)
     for c in range(W):
         b.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
+    b.stats(tv, tq, chunk=CHUNK)  # warm-up of the statistics path too (scratch allocation)
     barrier()
 
     # ---- timed region: K fused launches + the final statistics all-reduce ----
@@ -312,7 +320,6 @@ def run_b200(args):
         c = W + i
         b.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
         ev[i + 1].record(stream)
-    tv, tq = synth.truth_state_at(truth, n_chunks_run * Tc - 1)
     local_chunks, _ = b.stats(tv, tq, chunk=CHUNK)
     n_local = local_chunks.shape[0]
     table = allreduce_chunks(local_chunks, rank * n_local, world * n_local, device=dev if world > 1 else None)
@@ -410,12 +417,19 @@ def run_b200(args):
                        "l2_policy": f"every step reads a fresh {in_bytes / 1e6:.0f} MB input chunk (> 126 MB L2); all {n_chunks_run} chunks resident in HBM",
                        "stats_allreduce": "nccl, inside the timed region" if world > 1 else "single GPU, inside the timed region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
-                         "traffic": None, "kernel": "rbis_fused_kernel", "kernel_ms": k_ms,
+                         "traffic": NCU_TRAFFIC["bytes"] if (N, Tc) == (NCU_TRAFFIC["filters"], NCU_TRAFFIC["chunk_steps"]) else None,
+                         "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic: %d input + %d state bytes" % (in_bytes, 2 * N * 8 * (231 + 26)),
+                         "kernel": "rbis_fused_kernel", "kernel_ms": k_ms,
                          "algorithmic_flops_per_filter_step": flops_chunk / (N * Tc),
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "nominal_peak": NOMINAL_FP64_TFLOPS, "dmma_peak_measured": dmma_tf,
                          "hbm_stream_gbs": in_bytes / (k_ms * 1e-3) / 1e9,
-                         "note": "achieved counts the dense algorithmic flops of SURVEY.md 8d; the kernel exploits the block structure of Ad and symmetry of P and executes fewer"},
+                         "executed_flops_per_filter_step": 2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"],
+                         "achieved_hw": (2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * N * Tc / (k_ms * 1e-3) / 1e12,
+                         "frac_hw": (2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * N * Tc / (k_ms * 1e-3) / 1e12 / dfma_tf,
+                         "fp64_pipe_busy_frac": (EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * 2 * N * Tc / 32 / (k_ms * 1e-3) / (148 * 4 * 1.965e9),
+                         "executed_source": EXECUTED["source"],
+                         "note": "achieved/frac count the dense ALGORITHMIC flops of SURVEY.md 8d (task contract); the kernel exploits the block structure of Ad and the symmetry of P and executes ~11x fewer, so frac exceeds 1. achieved_hw/frac_hw count executed flops; fp64_pipe_busy_frac = executed FP64 warp-instructions x 2 issue cycles / (SM sub-partition cycles), cf. ncu sm__pipe_fp64_cycles_active in profiles/"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "ensemble": {"mean_nees9": summ["mean_nees"], "nees_in_95pct": summ["nees_in_95pct"], "non_finite": summ["non_finite"]},
         }
