@@ -142,27 +142,76 @@ def initial_state(N, gen, dev):
 
 
 class ClockSampler:
-    """nvidia-smi sampling of SM clocks and throttle reasons during the timed region."""
+    """SM clock / throttle-reason sampling during the timed region.  NVML in-process (pynvml) every 20 ms --
+    far less intrusive than polling the nvidia-smi binary, which showed up as 5-10 ms hiccups inside the timed
+    region; nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.stop_flag = index, [], None, None, False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            for _ in range(2):  # the first queries are slow (tens of ms): take them before the timed region
+                pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+                pynvml.nvmlDeviceGetPowerUsage(self.handle)
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
+
+    def poll_while(self, busy, period=0.008):
+        """NVML path: sample from the CALLING thread while busy() holds (the host only waits for the GPU during
+        that time, so the queries cannot delay host-side work of the timed region).  No-op on the nvidia-smi path."""
+        nv = self.nv
+        if nv is None:
+            return
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while busy():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.time(), sm, pw, [n for n, b in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0, t1):
+        if self.nv is not None:
+            rows = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + 0.02] or self.rows
+            if not rows:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+            sm = sorted(r[1] for r in rows)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "power_w_max": max(r[2] for r in rows), "samples": len(rows),
+                    "reasons": sorted({n for r in rows for n in r[3]}), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -177,7 +226,7 @@ class ClockSampler:
                 if r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
-                "samples": len(rows), "reasons": sorted(reasons)}
+                "samples": len(rows), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,6 +369,7 @@ def run_b200(args):
         c = W + i
         b.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
         ev[i + 1].record(stream)
+    sampler.poll_while(lambda: not ev[max(K - 2, 0)].query())  # clocks under load; stops two launches before the end
     local_chunks, _ = b.stats(tv, tq, chunk=CHUNK)
     n_local = local_chunks.shape[0]
     table = allreduce_chunks(local_chunks, rank * n_local, world * n_local, device=dev if world > 1 else None)
@@ -331,6 +381,8 @@ def run_b200(args):
     launches = b.launch_count - launches0
     total_ms = ev[0].elapsed_time(end)
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    log(f"[rank {rank}] fused launches: min {min(kernel_ms):.3f} mean {np.mean(kernel_ms):.3f} max {max(kernel_ms):.3f} ms; "
+        f"statistics + all-reduce tail {ev[K].elapsed_time(end):.3f} ms; total {total_ms:.3f} ms")
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
