@@ -19,6 +19,7 @@ rows (all chunks of the run are resident in HBM, far larger than L2), the state 
 --impl reference times that CPU path alone on the same workload shape.
 """
 import argparse
+import gc
 import json
 import math
 import os
@@ -62,6 +63,7 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--launch-groups", type=int, default=0, help="0 = library default (automatic)")
     return ap.parse_args()
 
 
@@ -182,7 +184,11 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def poll_while(self, busy, period=0.008):
+    def sample_once(self):
+        """One NVML sample from the calling thread (used between launches: the host runs ahead of the GPU there)."""
+        self.poll_while(lambda: True, period=0.0, max_samples=1)
+
+    def poll_while(self, busy, period=0.008, stop_after=1e9, max_samples=1 << 30):
         """NVML path: sample from the CALLING thread while busy() holds (the host only waits for the GPU during
         that time, so the queries cannot delay host-side work of the timed region).  No-op on the nvidia-smi path."""
         nv = self.nv
@@ -190,7 +196,10 @@ class ClockSampler:
             return
         bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
-        while busy():
+        t_stop = time.time() + stop_after
+        taken = 0
+        while busy() and time.time() < t_stop and taken < max_samples:
+            taken += 1
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
@@ -198,7 +207,8 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, pw, [n for n, b in bits if mask & b]))
             except Exception:
                 pass
-            time.sleep(period)
+            if period > 0:
+                time.sleep(period)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -337,7 +347,7 @@ def run_b200(args):
     def streams_of(ch):
         return [MeasStream(synth.LEGODO_IDX, ch["legodo"], R_lego), MeasStream(synth.POSE_IDX, ch["pose_z"], R_pose, quat=ch["pose_q"])]
 
-    b = RBISBatch(N, device=local)
+    b = RBISBatch(N, device=local, launch_groups=args.launch_groups)
     b.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
     b.set_state(vec0, quat0, cov0)
     b.synchronize()
@@ -351,38 +361,59 @@ def run_b200(args):
 
     # ---- warm-up ----
     tv, tq = synth.truth_state_at(truth, n_chunks_run * Tc - 1)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record(stream)
     for c in range(W):
         b.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
-    b.stats(tv, tq, chunk=CHUNK)  # warm-up of the statistics path too (scratch allocation)
+    b.record()
+    w1.record(stream)
+    wl, _ = b.stats(tv, tq, chunk=CHUNK)  # warm-up of the statistics path too (scratch allocation, first-call costs)
+    allreduce_chunks(wl, rank * wl.shape[0], world * wl.shape[0], device=dev if world > 1 else None)
     barrier()
+    est_launch_s = 1e-3 * w0.elapsed_time(w1) / max(W, 1)  # only used to stop the clock polling early enough
 
     # ---- timed region: K fused launches + the final statistics all-reduce ----
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     launches0 = b.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    # Consecutive fused launches overlap (launch groups, include/rbis_batch.h), so a per-launch event pair would not
+    # bracket one launch's work: the K launches are timed as one region on the library's stream (b.record() makes that
+    # stream join the internal group streams) and the mean launch duration is region / K.
+    ev0, evk = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    gc.collect()
+    gc.disable()
     t_wall0 = time.time()
-    ev[0].record(stream)
+    ev0.record(stream)
     for i in range(K):
         c = W + i
         b.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
-        ev[i + 1].record(stream)
-    sampler.poll_while(lambda: not ev[max(K - 2, 0)].query())  # clocks under load; stops two launches before the end
+        if i >= 2 and i % 3 == 2 and i < K - 1:
+            sampler.sample_once()  # clocks under load; the host is several launches ahead of the GPU here
+    t_h0 = time.time()
+    b.record()
+    evk.record(stream)
+    t_h1 = time.time()
+    t_h2 = time.time()
     local_chunks, _ = b.stats(tv, tq, chunk=CHUNK)
+    t_h3 = time.time()
     n_local = local_chunks.shape[0]
     table = allreduce_chunks(local_chunks, rank * n_local, world * n_local, device=dev if world > 1 else None)
     end = torch.cuda.Event(enable_timing=True)
     end.record(stream)
+    t_h4 = time.time()
+    log(f"[rank {rank}] host timeline (ms since start): enqueue done {1e3 * (t_h0 - t_wall0):.2f}, record {1e3 * (t_h1 - t_wall0):.2f}, "
+        f"poll end {1e3 * (t_h2 - t_wall0):.2f}, stats returned {1e3 * (t_h3 - t_wall0):.2f}, end recorded {1e3 * (t_h4 - t_wall0):.2f}")
     barrier()
+    gc.enable()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = b.launch_count - launches0
-    total_ms = ev[0].elapsed_time(end)
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
-    log(f"[rank {rank}] fused launches: min {min(kernel_ms):.3f} mean {np.mean(kernel_ms):.3f} max {max(kernel_ms):.3f} ms; "
-        f"statistics + all-reduce tail {ev[K].elapsed_time(end):.3f} ms; total {total_ms:.3f} ms")
+    total_ms = ev0.elapsed_time(end)
+    kernel_ms = [ev0.elapsed_time(evk) / K]
+    log(f"[rank {rank}] {K} fused launches: {ev0.elapsed_time(evk):.3f} ms = {kernel_ms[0]:.3f} ms per launch; "
+        f"statistics + all-reduce tail {evk.elapsed_time(end):.3f} ms; total {total_ms:.3f} ms")
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -76,6 +76,11 @@ typedef struct {
                               1 = renormalise the quaternion after every applied delta */
   int32_t snapshot_slots;  /* ring slots for RBIS_OP_SNAPSHOT / RESTORE; 0 = none */
   int32_t device;          /* CUDA device ordinal */
+  int32_t launch_groups;   /* fused launches are split into this many CTA ranges on separate streams so that
+                              consecutive rbis_batch_run_fused calls overlap and the last, partially filled wave of
+                              one launch does not idle SMs; 0 = automatic (4 when the CTAs do not fill whole
+                              waves, else 1), 1 = off, max 8 */
+  int32_t reserved;
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /
@@ -111,7 +116,9 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
 int rbis_batch_destroy(rbis_batch_t* h);
 int rbis_batch_synchronize(rbis_batch_t* h);
 int64_t rbis_batch_num_filters(const rbis_batch_t* h);
-/* Raw CUDA stream (cudaStream_t) the handle computes on, for event timing by the caller. */
+/* Raw CUDA stream (cudaStream_t) of the handle, for event timing by the caller.  With launch groups the fused
+ * kernels run on internal streams that this stream joins at the next non-fused call: to time fused work, call
+ * rbis_batch_record() (it joins) and then record the timing event on this stream. */
 void* rbis_batch_stream(rbis_batch_t* h);
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t rbis_batch_launch_count(const rbis_batch_t* h);

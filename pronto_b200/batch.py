@@ -70,13 +70,14 @@ class RBISBatch:
     """An ensemble of N RBIS filters on one GPU (rbis_batch_t)."""
 
     def __init__(self, n_filters, device=0, g_val=9.8, chi_tol=1e-6, ctor_folds_chi=True, renormalize_quat=False,
-                 snapshot_slots=0):
+                 snapshot_slots=0, launch_groups=0):
         self.lib = capi.load()
         cfg = capi.Config()
         self.lib.rbis_default_config(C.byref(cfg))
         cfg.g_val, cfg.chi_tol = float(g_val), float(chi_tol)
         cfg.ctor_folds_chi, cfg.renormalize_quat = int(bool(ctor_folds_chi)), int(bool(renormalize_quat))
         cfg.snapshot_slots, cfg.device = int(snapshot_slots), int(device)
+        cfg.launch_groups = int(launch_groups)
         self.h = C.c_void_p()
         capi.check(self.lib.rbis_batch_create(C.byref(self.h), int(n_filters), C.byref(cfg)))
         self.N = int(n_filters)

@@ -32,6 +32,8 @@ class Config(C.Structure):
         ("renormalize_quat", C.c_int32),
         ("snapshot_slots", C.c_int32),
         ("device", C.c_int32),
+        ("launch_groups", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

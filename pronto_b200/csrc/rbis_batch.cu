@@ -62,6 +62,7 @@ struct StagingSlot {  // device copies of caller-host input arrays for one fused
   DevBuf imu;
   DevBuf z[RBIS_MAX_STREAMS], quat[RBIS_MAX_STREAMS], rdiag[RBIS_MAX_STREAMS];
   cudaEvent_t copied = nullptr, consumed = nullptr;
+  int ring = -1;  // grouped launches: ring slot whose group events mark the consumption of this staging slot
 };
 
 }  // namespace
@@ -96,6 +97,24 @@ struct rbis_batch {
   double* d_rshared = nullptr;  // [MAX_STREAMS][81]
   StagingSlot slots[2];
   int slot_toggle = 0;
+  // ---- launch groups: the ensemble's CTAs are split into n_groups contiguous ranges, each launched on its own
+  // stream, so that consecutive fused launches overlap (group g of launch k+1 starts when group g of launch k
+  // is done) and the partially filled last wave of a launch does not idle SMs.  n_groups == 1: plain path.
+  static constexpr int kMaxGroups = 8, kRing = 4;
+  int n_groups = 1;
+  cudaStream_t gstream[kMaxGroups] = {};
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t gdone[kRing][kMaxGroups] = {};  // completion of group g of the launch that used ring slot r
+  bool gdone_valid[kRing] = {};
+  cudaEvent_t uploaded[kRing] = {};
+  cudaEvent_t pre_evt = nullptr;
+  rbisk::Op* d_ops_ring[kRing] = {};
+  size_t d_ops_ring_cap[kRing] = {};
+  double* d_rshared_ring[kRing] = {};
+  int64_t launch_seq = 0;
+  int last_ring = -1;
+  bool groups_dirty = false;  // group streams hold work the main stream has not joined
+  bool stream_dirty = true;   // the main stream got work since the last grouped launch
   cudaEvent_t tickets[8] = {};
   int next_ticket = 0;
   int smem_bytes = 0;
@@ -108,6 +127,17 @@ constexpr int kSmemBytes = rbisk::SMEM_BYTES;
 int use_device(const rbis_batch* h) {
   cudaError_t e = cudaSetDevice(h->cfg.device);
   if (e != cudaSuccess) return fail(RBIS_ERR_CUDA, "cudaSetDevice(%d): %s", h->cfg.device, cudaGetErrorString(e));
+  return 0;
+}
+
+// Every entry point that enqueues work on the main stream calls this first: the main stream joins the group
+// streams (so it sees the results of grouped launches), and the next grouped launch will wait for it.
+int main_stream_work(rbis_batch* h) {
+  if (h->groups_dirty) {
+    for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->gdone[h->last_ring][g], 0));
+    h->groups_dirty = false;
+  }
+  h->stream_dirty = true;
   return 0;
 }
 
@@ -229,7 +259,18 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   h->slot_toggle ^= 1;
   cudaStream_t cst = h->copy_stream;
   const bool staging = (mem == RBIS_MEM_HOST);
-  if (staging) CUDA_TRY(cudaStreamWaitEvent(cst, slot.consumed, 0));
+  const bool grouped = h->n_groups > 1;
+  const int ring = (int)(h->launch_seq % rbis_batch::kRing);
+  if (staging) {
+    if (grouped && slot.ring >= 0) {
+      for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(cst, h->gdone[slot.ring][g], 0));
+    } else {
+      CUDA_TRY(cudaStreamWaitEvent(cst, slot.consumed, 0));
+    }
+  }
+  if (grouped && h->gdone_valid[ring]) {  // ring slot reuse: the launch that used it (4 launches ago) must be done
+    for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaEventSynchronize(h->gdone[ring][g]));
+  }
   if (imu) {
     if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * N, mem, cst, &kp.imu)) return rc;
   }
@@ -256,41 +297,81 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * N, mem, cst, &d.quat)) return rc;
     if (in.r_mode == RBIS_R_SHARED_FULL) {
       std::memcpy(&rshared[(size_t)s * 81], in.R, sizeof(double) * in.m * in.m);
-      d.R = h->d_rshared + (size_t)s * 81;
+      d.R = (grouped ? h->d_rshared_ring[ring] : h->d_rshared) + (size_t)s * 81;
       any_shared = true;
     } else {
       if (int rc = copy_in(h, slot.rdiag[s], in.R, (size_t)in.m * N, mem, cst, &d.R)) return rc;
     }
   }
-  if (staging) {
-    CUDA_TRY(cudaEventRecord(slot.copied, cst));
-    CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
-  }
-
-  // ---- op table and shared R matrices (small, pageable source: staged synchronously by the runtime) ----
-  if ((size_t)n_ops > h->d_ops_cap) {
-    if (h->d_ops) {
-      CUDA_TRY(cudaStreamSynchronize(h->stream));
-      cudaFree(h->d_ops);
-      h->d_ops = nullptr;
-      h->d_ops_cap = 0;
-    }
-    size_t cap = (size_t)n_ops * 2;
-    if (cap < 1024) cap = 1024;
-    CUDA_TRY(cudaMalloc(&h->d_ops, cap * sizeof(rbisk::Op)));
-    h->d_ops_cap = cap;
-  }
-  CUDA_TRY(cudaMemcpyAsync(h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->stream));
-  if (any_shared)
-    CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  kp.ops = h->d_ops;
-
+  if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
   const unsigned grid = (unsigned)((N + rbisk::TPB - 1) / rbisk::TPB);
-  if (needs_general) rbisk::rbis_fused_kernel<true><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
-  else rbisk::rbis_fused_kernel<false><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
-  if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
+  if (!grouped) {
+    if (int rc = main_stream_work(h)) return rc;
+    if (staging) CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
+    // ---- op table and shared R matrices (small, pageable source: staged synchronously by the runtime) ----
+    if ((size_t)n_ops > h->d_ops_cap) {
+      if (h->d_ops) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_ops);
+        h->d_ops = nullptr;
+        h->d_ops_cap = 0;
+      }
+      size_t cap = (size_t)n_ops * 2;
+      if (cap < 1024) cap = 1024;
+      CUDA_TRY(cudaMalloc(&h->d_ops, cap * sizeof(rbisk::Op)));
+      h->d_ops_cap = cap;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->stream));
+    if (any_shared)
+      CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    kp.ops = h->d_ops;
+    kp.block_offset = 0;
+    if (needs_general) rbisk::rbis_fused_kernel<true><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+    else rbisk::rbis_fused_kernel<false><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
+  } else {
+    // ---- grouped launch: uploads on their own stream into this launch's ring slot, one kernel per group ----
+    if ((size_t)n_ops > h->d_ops_ring_cap[ring]) {
+      if (h->d_ops_ring[ring]) cudaFree(h->d_ops_ring[ring]);  // idle: its last user was synchronised above
+      h->d_ops_ring[ring] = nullptr;
+      h->d_ops_ring_cap[ring] = 0;
+      size_t cap = (size_t)n_ops * 2;
+      if (cap < 1024) cap = 1024;
+      CUDA_TRY(cudaMalloc(&h->d_ops_ring[ring], cap * sizeof(rbisk::Op)));
+      h->d_ops_ring_cap[ring] = cap;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_ops_ring[ring], kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->upload_stream));
+    if (any_shared)
+      CUDA_TRY(cudaMemcpyAsync(h->d_rshared_ring[ring], rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->upload_stream));
+    CUDA_TRY(cudaEventRecord(h->uploaded[ring], h->upload_stream));
+    kp.ops = h->d_ops_ring[ring];
+    const bool wait_main = h->stream_dirty;
+    if (wait_main) CUDA_TRY(cudaEventRecord(h->pre_evt, h->stream));
+    const unsigned per = (grid + (unsigned)h->n_groups - 1) / (unsigned)h->n_groups;
+    for (int g = 0; g < h->n_groups; g++) {
+      const unsigned b0 = (unsigned)g * per, b1 = b0 + per < grid ? b0 + per : grid;
+      cudaStream_t gs = h->gstream[g];
+      if (wait_main) CUDA_TRY(cudaStreamWaitEvent(gs, h->pre_evt, 0));
+      if (staging) CUDA_TRY(cudaStreamWaitEvent(gs, slot.copied, 0));
+      CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
+      if (b1 > b0) {
+        kp.block_offset = (int)b0;
+        if (needs_general) rbisk::rbis_fused_kernel<true><<<b1 - b0, rbisk::TPB, kSmemBytes, gs>>>(kp);
+        else rbisk::rbis_fused_kernel<false><<<b1 - b0, rbisk::TPB, kSmemBytes, gs>>>(kp);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      }
+      CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
+    }
+    h->gdone_valid[ring] = true;
+    h->last_ring = ring;
+    h->groups_dirty = true;
+    h->stream_dirty = false;
+    if (staging) slot.ring = ring;
+  }
+  h->launch_seq++;
   h->snap_valid = snap_valid;
   h->utime = last_utime;
   return 0;
@@ -310,6 +391,8 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->renormalize_quat = 0;
   cfg->snapshot_slots = 0;
   cfg->device = 0;
+  cfg->launch_groups = 0;
+  cfg->reserved = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -319,6 +402,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   rbis_batch_config_t c;
   if (cfg) c = *cfg; else rbis_default_config(&c);
   if (c.snapshot_slots < 0) return fail(RBIS_ERR_INVALID, "snapshot_slots must be >= 0");
+  if (c.launch_groups < 0 || c.launch_groups > rbis_batch::kMaxGroups)
+    return fail(RBIS_ERR_INVALID, "launch_groups must be in [0, %d]", rbis_batch::kMaxGroups);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -352,6 +437,24 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   } while (0)
   CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  {
+    // launch groups: explicit, or automatic = 4 when the CTAs do not fill a whole number of waves
+    const long long ctas = (long long)((n_filters + rbisk::TPB - 1) / rbisk::TPB), sms = prop.multiProcessorCount;
+    int g = c.launch_groups;
+    if (g == 0) g = (ctas > sms && ctas % sms != 0) ? 4 : 1;
+    if ((long long)g > ctas) g = (int)ctas;
+    h->n_groups = g < 1 ? 1 : g;
+  }
+  if (h->n_groups > 1) {
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->pre_evt, cudaEventDisableTiming));
+    for (int g = 0; g < h->n_groups; g++) CREATE_TRY(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    for (int r = 0; r < rbis_batch::kRing; r++) {
+      CREATE_TRY(cudaEventCreateWithFlags(&h->uploaded[r], cudaEventDisableTiming));
+      for (int g = 0; g < h->n_groups; g++) CREATE_TRY(cudaEventCreateWithFlags(&h->gdone[r][g], cudaEventDisableTiming));
+      CREATE_TRY(cudaMalloc(&h->d_rshared_ring[r], (size_t)RBIS_MAX_STREAMS * 81 * sizeof(double)));
+    }
+  }
   for (auto& s : h->slots) {
     CREATE_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
@@ -388,6 +491,17 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->upload_stream) { cudaStreamSynchronize(h->upload_stream); cudaStreamDestroy(h->upload_stream); }
+  for (int g = 0; g < rbis_batch::kMaxGroups; g++)
+    if (h->gstream[g]) { cudaStreamSynchronize(h->gstream[g]); cudaStreamDestroy(h->gstream[g]); }
+  for (int r = 0; r < rbis_batch::kRing; r++) {
+    if (h->uploaded[r]) cudaEventDestroy(h->uploaded[r]);
+    for (int g = 0; g < rbis_batch::kMaxGroups; g++)
+      if (h->gdone[r][g]) cudaEventDestroy(h->gdone[r][g]);
+    cudaFree(h->d_ops_ring[r]);
+    cudaFree(h->d_rshared_ring[r]);
+  }
+  if (h->pre_evt) cudaEventDestroy(h->pre_evt);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared);
   h->full_cov.release(); h->misc.release(); h->stats_async.release();
@@ -409,7 +523,9 @@ int rbis_batch_destroy(rbis_batch_t* h) {
 int rbis_batch_synchronize(rbis_batch_t* h) {
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+  if (h->upload_stream) CUDA_TRY(cudaStreamSynchronize(h->upload_stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -424,6 +540,7 @@ int rbis_batch_set_state(rbis_batch_t* h, const double* vec, const double* quat,
   if (!vec || !quat) return fail(RBIS_ERR_INVALID, "vec and quat are required");
   if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t N = (size_t)h->N;
   const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   CUDA_TRY(cudaMemcpyAsync(h->vec, vec, N * 21 * sizeof(double), kind, h->stream));
@@ -451,6 +568,7 @@ int rbis_batch_get_state(rbis_batch_t* h, double* vec, double* quat, double* cov
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t N = (size_t)h->N;
   const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (vec) CUDA_TRY(cudaMemcpyAsync(vec, h->vec, N * 21 * sizeof(double), kind, h->stream));
@@ -477,6 +595,7 @@ int rbis_batch_set_filter(rbis_batch_t* h, int64_t n, const double* vec, const d
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n < 0 || n >= h->N) return fail(RBIS_ERR_INVALID, "filter index out of range");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t pitch = (size_t)h->N * sizeof(double);
   if (vec) CUDA_TRY(cudaMemcpy2DAsync(h->vec + n, pitch, vec, sizeof(double), sizeof(double), 21, cudaMemcpyHostToDevice, h->stream));
   if (quat) CUDA_TRY(cudaMemcpy2DAsync(h->quat + n, pitch, quat, sizeof(double), sizeof(double), 4, cudaMemcpyHostToDevice, h->stream));
@@ -495,6 +614,7 @@ int rbis_batch_get_filter(rbis_batch_t* h, int64_t n, double* vec, double* quat,
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n < 0 || n >= h->N) return fail(RBIS_ERR_INVALID, "filter index out of range");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t pitch = (size_t)h->N * sizeof(double);
   double packed[rbisk::NP];
   if (vec) CUDA_TRY(cudaMemcpy2DAsync(vec, sizeof(double), h->vec + n, pitch, sizeof(double), 21, cudaMemcpyDeviceToHost, h->stream));
@@ -512,6 +632,7 @@ int rbis_batch_set_process_noise(rbis_batch_t* h, double q_gyro, double q_accel,
                                  double q_accel_bias) {
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const long long N = h->N;
   const double q[4] = {q_gyro, q_accel, q_gyro_bias, q_accel_bias};
   for (int k = 0; k < 4; k++) {
@@ -527,6 +648,7 @@ int rbis_batch_set_process_noise_per_filter(rbis_batch_t* h, const double* q_gyr
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (!q_gyro || !q_accel || !q_gyro_bias || !q_accel_bias) return fail(RBIS_ERR_INVALID, "all four arrays are required");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t N = (size_t)h->N;
   const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const double* src[4] = {q_gyro, q_accel, q_gyro_bias, q_accel_bias};
@@ -545,6 +667,7 @@ int rbis_batch_ins_step(rbis_batch_t* h, const double* gyro, const double* accel
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (!gyro || !accel) return fail(RBIS_ERR_INVALID, "gyro and accel are required");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   // assemble one [6][N] IMU row on the device
   const size_t N = (size_t)h->N;
   if (h->misc.ensure(6 * N)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
@@ -587,6 +710,7 @@ int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* tru
   if (!truth_vec || !truth_quat || !out_chunks) return fail(RBIS_ERR_INVALID, "truth and out_chunks are required");
   if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t N = (size_t)h->N;
   const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
   // scratch: truth (25 or 25N) + per-filter [23][N] + chunks [nch][96]
@@ -623,6 +747,7 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
   if (!truth_vec || !truth_quat || !out_chunks) return fail(RBIS_ERR_INVALID, "truth and out_chunks are required");
   if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const size_t N = (size_t)h->N;
   const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
   // separate scratch from rbis_batch_stats so that a pending enqueue is never disturbed by a resize
@@ -645,6 +770,7 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
 int rbis_batch_record(rbis_batch_t* h, int32_t* ticket) {
   if (!h || !ticket) return fail(RBIS_ERR_INVALID, "null handle or ticket");
   if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
   const int t = h->next_ticket;
   h->next_ticket = (t + 1) % 8;
   CUDA_TRY(cudaEventRecord(h->tickets[t], h->stream));

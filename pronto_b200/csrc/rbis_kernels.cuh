@@ -42,6 +42,9 @@
 #ifndef RBIS_STAGE_FENCE
 #define RBIS_STAGE_FENCE 0  // 1: compiler memory fence after every column stage (bounds shared-memory load hoisting)
 #endif
+#ifndef RBIS_EARLY_LOADS
+#define RBIS_EARLY_LOADS 1
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -50,7 +53,10 @@ namespace rbisk {
 
 constexpr int NS = 21;       // rbis_num_states
 constexpr int NP = 231;      // packed upper triangle
-constexpr int TPB = 256;     // filters (= threads) per CTA
+#ifndef RBIS_TPB
+#define RBIS_TPB 256
+#endif
+constexpr int TPB = RBIS_TPB;     // filters (= threads) per CTA
 constexpr int MAX_MEAS = 9;
 constexpr int MAX_STREAMS = 8;
 constexpr int MAX_CHUNKS = 9;
@@ -142,6 +148,7 @@ struct KParams {
   long long n_ops;
   double g_val, chi_tol;
   int ctor_folds_chi, renorm, n_snap;
+  int block_offset;  // first CTA of this launch's range (launch groups)
   StreamDesc streams[MAX_STREAMS];
 };
 
@@ -254,6 +261,19 @@ __device__ __forceinline__ void tm_settle_d(double& d) {
   asm volatile("" : "+d"(d));
 #else
   (void)d;
+#endif
+}
+
+// Input loads that must be ISSUED where they are written (top of an op) and consumed a few thousand
+// cycles later: volatile, so ptxas cannot sink them next to their first use to save registers, which is
+// what it does with plain __ldg and what exposed the full HBM latency once per op.
+__device__ __forceinline__ double ldg_early(const double* ptr) {
+#if RBIS_EARLY_LOADS
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  return v;
+#else
+  return __ldg(ptr);
 #endif
 }
 
@@ -657,10 +677,10 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   // issue the measurement loads first; they are consumed after the covariance work
   double z[3], Rdg[3];
 #pragma unroll
-  for (int a = 0; a < 3; a++) z[a] = __ldg(st.z + (row * st.m + (a0 + a)) * N + n);
+  for (int a = 0; a < 3; a++) z[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * N + n);
   if (st.r_mode == 1) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) Rdg[a] = __ldg(st.R + (long long)(a0 + a) * N + n);
+    for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
   }
   // Y starts as HP = P[idx, :]
   double Y[3][NS];
@@ -915,7 +935,7 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   const uint32_t tm_base = tm_base_s;
 
   const long long N = p.N;
-  long long n = (long long)blockIdx.x * TPB + tid;
+  long long n = ((long long)blockIdx.x + p.block_offset) * TPB + tid;
   const bool active = n < N;
   if (!active) n = N - 1;  // idle lanes shadow the last filter and never store
 
@@ -928,15 +948,28 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   s.ll = p.loglik[n];
   cov_load_all(P, p.P + n, N);
 
-  Op op_next = p.ops[0];
+  auto load_op = [&](long long i) {
+    Op o;
+#if RBIS_EARLY_LOADS
+    long long w0, w1;  // Op is 24 bytes: three 8-byte loads
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(w0) : "l"(reinterpret_cast<const long long*>(p.ops + i)));
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(w1) : "l"(reinterpret_cast<const long long*>(p.ops + i) + 1));
+    o.kind = (int)(w0 & 0xffffffffll); o.stream = (int)(w0 >> 32); o.row = w1;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(o.dt) : "l"(&p.ops[i].dt));
+#else
+    o = p.ops[i];
+#endif
+    return o;
+  };
+  Op op_next = load_op(0);
   for (long long oi = 0; oi < p.n_ops; oi++) {
     const Op op = op_next;
-    if (oi + 1 < p.n_ops) op_next = p.ops[oi + 1];  // fetched one op ahead: its latency hides behind this op
+    if (oi + 1 < p.n_ops) op_next = load_op(oi + 1);  // fetched one op ahead: its latency hides behind this op
     if (op.kind == 0) {
       // ---- IMU process step ----
       const double* base = p.imu + op.row * 6 * N + n;
-      const V3 gyro{__ldg(base), __ldg(base + N), __ldg(base + 2 * N)};
-      const V3 acc{__ldg(base + 3 * N), __ldg(base + 4 * N), __ldg(base + 5 * N)};
+      const V3 gyro{ldg_early(base), ldg_early(base + N), ldg_early(base + 2 * N)};
+      const V3 acc{ldg_early(base + 3 * N), ldg_early(base + 4 * N), ldg_early(base + 5 * N)};
       const double q_gyro = __ldg(p.q_gyro + n), q_accel = __ldg(p.q_accel + n), q_gyro_bias = __ldg(p.q_gyro_bias + n),
                    q_accel_bias = __ldg(p.q_accel_bias + n);
       const double dt = op.dt;
