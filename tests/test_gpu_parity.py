@@ -447,3 +447,51 @@ def test_full_size_ensemble_replication_property(oracle):
     # covariance stays symmetric positive definite on the measured block
     P = gP[:, 5].reshape(21, 21)
     assert np.array_equal(P, P.T) and np.all(np.linalg.eigvalsh(P[3:12, 3:12]) > 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# launch groups (CTA ranges on separate streams, consecutive launches overlap)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_launch_groups_do_not_change_results_and_keep_call_order(oracle):
+    from pronto_b200.batch import make_ops
+
+    """A >148-CTA ensemble run as 3 consecutive fused launches with launch_groups = 1 / automatic / 8 gives
+    bit-identical states, also when reads (get_state, stats) and writes (set_process_noise) sit between the
+    launches -- the main stream must join the group streams and the next launch must wait for it."""
+    N, T = 148 * 256 + 700, 12
+    sc = scenario(64, 3 * T)
+    st = sc["st"]
+    rep = lambda a: np.ascontiguousarray(np.tile(a, (1,) * (a.ndim - 1) + (N // 64 + 1,))[..., :N])
+    vec, quat, cov = rep(sc["vec"]), rep(sc["quat"]), rep(sc["cov"])
+    imu, lego, pz, pq = rep(st["imu"]), rep(st["legodo"]), rep(st["pose_z"]), rep(st["pose_q"])
+    ev = st["events"]
+    cuts = [0, len(ev) // 3, 2 * len(ev) // 3, len(ev)]
+    outs = []
+    for groups in (1, 0, 8):
+        with RBISBatch(N, launch_groups=groups) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(vec, quat, cov)
+            mids = []
+            for k in range(3):
+                ops = make_ops(ev[cuts[k]:cuts[k + 1]])
+                b.run_fused(ops, imu=imu, streams=[MeasStream(synth.LEGODO_IDX, lego, st["R_legodo"]),
+                                                   MeasStream(synth.POSE_IDX, pz, st["R_pose"], quat=pq)])
+                if k == 0:
+                    mids.append(b.get_state(cov=False)[0].copy())      # read between launches
+                if k == 1:
+                    q = nominal_q()
+                    b.set_process_noise(q[0] * 1.5, q[1], q[2], q[3])  # write between launches
+            outs.append((b.get_state(), mids[0]))
+    (g1, m1), (g0, m0), (g8, m8) = outs
+    for a, c in ((g1, g0), (g1, g8)):
+        for x, y in zip(a[:4], c[:4]):
+            assert np.array_equal(x, y)
+    assert np.array_equal(m1, m0) and np.array_equal(m1, m8)
+    # and the replicated filters agree with the oracle on the first 64
+    ref = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st),
+                              ev[:cuts[2]], n_threads=NTHREADS)
+    q = nominal_q()
+    ref = oracle.run_ensemble(ref["vec"], ref["quat"], ref["cov"], ref["loglik"], ev[cuts[2] - 1][3], (q[0] * 1.5, q[1], q[2], q[3]),
+                              st["imu"], oracle_streams(st), ev[cuts[2]:], n_threads=NTHREADS)
+    _assert_close((g1[0][:, :64], g1[1][:, :64], g1[2][:, :64]), (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "groups")
