@@ -503,6 +503,7 @@ def run_b200(args):
                          "traffic": NCU_TRAFFIC["bytes"] if (N, Tc) == (NCU_TRAFFIC["filters"], NCU_TRAFFIC["chunk_steps"]) else None,
                          "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic: %d input + %d state bytes" % (in_bytes, 2 * N * 8 * (231 + 26)),
                          "kernel": "rbis_fused_kernel", "kernel_ms": k_ms,
+                         "kernel_ms_how": "CUDA events on the library stream around the K back-to-back fused launches (the stream joins the launch-group streams before the closing event), divided by K: launches overlap by design (launch groups), so a per-launch event pair would not bracket one launch",
                          "algorithmic_flops_per_filter_step": flops_chunk / (N * Tc),
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "nominal_peak": NOMINAL_FP64_TFLOPS, "dmma_peak_measured": dmma_tf,
