@@ -294,7 +294,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -517,14 +517,31 @@ def run_b200(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "ensemble": {"mean_nees9": summ["mean_nees"], "nees_in_95pct": summ["nees_in_95pct"], "non_finite": summ["non_finite"]},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     b.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else that lands on fd 1 (NCCL prints its
+    version banner there, torchrun its OMP note) was redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

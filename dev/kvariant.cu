@@ -35,15 +35,15 @@ void fill(void* blob, long long N, double* vec, double* quat, double* P, double*
   std::memset(&kp, 0, sizeof(kp));
   kp.N = N; kp.vec = vec; kp.quat = quat; kp.P = P; kp.loglik = ll;
   kp.q_gyro = q4; kp.q_accel = q4 + N; kp.q_gyro_bias = q4 + 2 * N; kp.q_accel_bias = q4 + 3 * N;
-  kp.imu = imu; kp.ops = (const VNAME::Op*)ops; kp.n_ops = n_ops; kp.g_val = 9.8; kp.chi_tol = 1e-6; kp.ctor_folds_chi = 1;
+  kp.imu = imu; kp.imu_cols = N; kp.ops = (const VNAME::Op*)ops; kp.n_ops = n_ops; kp.g_val = 9.8; kp.chi_tol = 1e-6; kp.ctor_folds_chi = 1;
   auto& s0 = kp.streams[0];
   s0.m = 3; s0.has_orient = 0; s0.r_mode = 0; s0.n_chunks = 1; s0.idx[0] = 3; s0.idx[1] = 4; s0.idx[2] = 5;
-  s0.chunk_start[0] = 0; s0.chunk_len[0] = 3; SET_FAST(s0, 0, 3); s0.z = z0; s0.R = R0;
+  s0.chunk_start[0] = 0; s0.chunk_len[0] = 3; SET_FAST(s0, 0, 3); s0.z = z0; s0.R = R0; s0.cols = N;
   auto& s1 = kp.streams[1];
   s1.m = 6; s1.has_orient = 1; s1.r_mode = 0; s1.n_chunks = 2;
   int idx[6] = {9, 10, 11, 6, 7, 8};
   for (int i = 0; i < 6; i++) s1.idx[i] = idx[i];
-  s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; SET_FAST(s1, 0, 9); SET_FAST(s1, 1, 6); s1.z = z1; s1.quat = q1; s1.R = R1;
+  s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; SET_FAST(s1, 0, 9); SET_FAST(s1, 1, 6); s1.z = z1; s1.quat = q1; s1.R = R1; s1.cols = N;
   std::memcpy(blob, &kp, sizeof(kp));
 }
 struct Reg { Reg() { registry().push_back({VTAG, VNAME::TPB, VNAME::SMEM_BYTES, launch, sizeof(VNAME::KParams), fill, prep}); } } reg;

@@ -14,7 +14,7 @@
  *       quat [4][N]    orientation (w,x,y,z)
  *       cov  [441][N]  RBIM, element (r,c) at row r + 21*c (Eigen column-major, MSE/rbis.hpp:30,123)
  *       imu  [rows][6][N]  gyro xyz then accelerometer xyz per IMU sample row
- *       z    [rows][m][N], meas quat [rows][4][N]
+ *       z    [rows][m][N], meas quat [rows][4][N]     (N -> cols under rbis_batch_set_column_map)
  *   - `mem` says where the caller's ensemble arrays live: host memory (copied by the library on the
  *     handle's stream; use pinned memory for truly asynchronous copies) or device memory (used in
  *     place; must stay valid until the call's work has completed).
@@ -156,6 +156,16 @@ int rbis_batch_indexed_update(rbis_batch_t* h, int m, const int32_t* idx, const 
 /* indexedPlusOrientationMeasurement + rbisApplyDelta (MSE/rbis.cpp:189-227).  quat [4][N]. */
 int rbis_batch_indexed_orient_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z,
                                      const double* quat, const double* R, int r_mode, int64_t utime, int mem);
+
+/* ---- column maps: filters that share input data (parameter sweeps in the style of the reference's noise
+ * identification, state-estimator/matlab/ins_noise_opt_script_mex.m:38-61, where every parameter point replays
+ * the SAME log; or one noise realisation evaluated under many parameter sets).  While a map is set, the
+ * corresponding array handed to rbis_batch_run_fused has `cols` columns instead of N and filter n reads column
+ * map[n]:  imu [rows][6][cols]  (which = -1),  z [rows][m][cols] and quat [rows][4][cols] of stream `which` >= 0.
+ * map: HOST int32[N] with entries in [0, cols), copied by the call; NULL restores the identity (cols ignored).
+ * Per-filter R ([m][N]) and everything else stay per filter.  The one-op entry points above ignore the maps.
+ * Synchronises the handle. */
+int rbis_batch_set_column_map(rbis_batch_t* h, int which, const int32_t* map, int64_t cols);
 
 /* ---- the fused hot path: run `n_ops` ops (host array, executed in order) for every filter in ONE
  * kernel launch, state and covariance resident on chip throughout.  This is the batch form of the

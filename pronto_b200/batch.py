@@ -185,6 +185,26 @@ class RBISBatch:
             mem = _common_mem([m1, m2, m3], "indexed_orient_update")
             capi.check(self.lib.rbis_batch_indexed_orient_update(self.h, m, idx_a, pz, pq, pr, r_mode, int(utime), mem))
 
+    # ---- shared input columns ----
+    def set_column_map(self, which, col_map=None, cols=0):
+        """Filter n reads column col_map[n] of the IMU array (which = -1) or of measurement stream `which`;
+        those arrays then have `cols` columns instead of N.  col_map=None restores the identity."""
+        k = int(which) + 1
+        if not hasattr(self, "_cols"):
+            self._cols = {}
+        if col_map is None:
+            capi.check(self.lib.rbis_batch_set_column_map(self.h, int(which), None, 0))
+            self._cols.pop(k, None)
+            return
+        m = np.ascontiguousarray(col_map, dtype=np.int32)
+        if m.shape != (self.N,):
+            raise ValueError("col_map must be int32[N]")
+        capi.check(self.lib.rbis_batch_set_column_map(self.h, int(which), m.ctypes.data, int(cols)))
+        self._cols[k] = int(cols)
+
+    def _ncols(self, which):
+        return getattr(self, "_cols", {}).get(int(which) + 1, self.N)
+
     # ---- fused program ----
     def run_fused(self, ops, imu=None, streams=()):
         """ops: structured array (OP_DTYPE) or iterable of (kind, stream, row, utime, dt)."""
@@ -194,8 +214,8 @@ class RBISBatch:
         mems = []
         p_imu, imu_rows = None, 0
         if imu is not None:
-            if imu.ndim != 3 or tuple(imu.shape[1:]) != (6, self.N):
-                raise ValueError("imu must be [rows][6][N]")
+            if imu.ndim != 3 or tuple(imu.shape[1:]) != (6, self._ncols(-1)):
+                raise ValueError("imu must be [rows][6][N] ([rows][6][cols] under a column map)")
             p_imu, mm = _ptr(imu, name="imu")
             imu_rows = int(imu.shape[0]); mems.append(mm)
         sarr = (capi.Stream * max(1, len(streams)))()
@@ -207,13 +227,13 @@ class RBISBatch:
             d.r_mode = capi.R_PER_FILTER_DIAG if st.per_filter_diag else capi.R_SHARED_FULL
             for a, i in enumerate(st.idx):
                 d.idx[a] = i
-            if st.z.ndim != 3 or tuple(st.z.shape[1:]) != (m, self.N):
-                raise ValueError(f"stream {s}: z must be [rows][{m}][N]")
+            if st.z.ndim != 3 or tuple(st.z.shape[1:]) != (m, self._ncols(s)):
+                raise ValueError(f"stream {s}: z must be [rows][{m}][N] (cols under a column map)")
             d.rows = int(st.z.shape[0])
             d.z, mm = _ptr(st.z, name="z"); mems.append(mm)
             if st.quat is not None:
-                if tuple(st.quat.shape) != (d.rows, 4, self.N):
-                    raise ValueError(f"stream {s}: quat must be [rows][4][N]")
+                if tuple(st.quat.shape) != (d.rows, 4, self._ncols(s)):
+                    raise ValueError(f"stream {s}: quat must be [rows][4][N] (cols under a column map)")
                 d.quat, mm = _ptr(st.quat, name="quat"); mems.append(mm)
             if st.per_filter_diag:
                 d.R, mm = _ptr(st.R, (m, self.N), "R"); mems.append(mm)

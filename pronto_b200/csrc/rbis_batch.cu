@@ -97,6 +97,9 @@ struct rbis_batch {
   double* d_rshared = nullptr;  // [MAX_STREAMS][81]
   StagingSlot slots[2];
   int slot_toggle = 0;
+  // ---- column maps: [0] = IMU, [1 + s] = measurement stream s (nullptr = identity, array has N columns)
+  int* d_map[1 + RBIS_MAX_STREAMS] = {};
+  int64_t map_cols[1 + RBIS_MAX_STREAMS] = {};
   // ---- launch groups: the ensemble's CTAs are split into n_groups contiguous ranges, each launched on its own
   // stream, so that consecutive fused launches overlap (group g of launch k+1 starts when group g of launch k
   // is done) and the partially filled last wave of a launch does not idle SMs.  n_groups == 1: plain path.
@@ -199,7 +202,7 @@ int copy_in(rbis_batch* h, DevBuf& buf, const double* src, size_t count, int mem
 }
 
 int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
-                 int n_streams, const rbis_stream_t* streams, int mem) {
+                 int n_streams, const rbis_stream_t* streams, int mem, bool use_maps = true) {
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(RBIS_ERR_INVALID, "bad op list");
   if (n_streams < 0 || n_streams > RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "n_streams out of range");
@@ -271,8 +274,10 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (grouped && h->gdone_valid[ring]) {  // ring slot reuse: the launch that used it (4 launches ago) must be done
     for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaEventSynchronize(h->gdone[ring][g]));
   }
+  kp.imu_map = use_maps ? h->d_map[0] : nullptr;
+  kp.imu_cols = kp.imu_map ? h->map_cols[0] : N;
   if (imu) {
-    if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * N, mem, cst, &kp.imu)) return rc;
+    if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * (size_t)kp.imu_cols, mem, cst, &kp.imu)) return rc;
   }
   std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * 81, 0.0);
   bool any_shared = false;
@@ -289,12 +294,14 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (in.r_mode != RBIS_R_SHARED_FULL && in.r_mode != RBIS_R_PER_FILTER_DIAG) return fail(RBIS_ERR_INVALID, "stream %d: bad r_mode", s);
     d.m = in.m; d.has_orient = in.has_orientation ? 1 : 0; d.r_mode = in.r_mode;
     for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
+    d.map = use_maps ? h->d_map[1 + s] : nullptr;
+    d.cols = d.map ? h->map_cols[1 + s] : N;
     if (in.rows == 0) { d.n_chunks = 0; continue; }
     plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
     mark_fast_chunks(d, &needs_general);
-    if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * N, mem, cst, &d.z)) return rc;
+    if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, &d.z)) return rc;
     if (in.has_orientation)
-      if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * N, mem, cst, &d.quat)) return rc;
+      if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
     if (in.r_mode == RBIS_R_SHARED_FULL) {
       std::memcpy(&rshared[(size_t)s * 81], in.R, sizeof(double) * in.m * in.m);
       d.R = (grouped ? h->d_rshared_ring[ring] : h->d_rshared) + (size_t)s * 81;
@@ -504,6 +511,7 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   if (h->pre_evt) cudaEventDestroy(h->pre_evt);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared);
+  for (auto& m : h->d_map) cudaFree(m);
   h->full_cov.release(); h->misc.release(); h->stats_async.release();
   for (auto& s : h->slots) {
     s.imu.release();
@@ -657,6 +665,28 @@ int rbis_batch_set_process_noise_per_filter(rbis_batch_t* h, const double* q_gyr
   return 0;
 }
 
+int rbis_batch_set_column_map(rbis_batch_t* h, int which, const int32_t* map, int64_t cols) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (which < -1 || which >= RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "which must be -1 (IMU) or a stream number");
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  const int k = which + 1;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // no launch may still read the old map
+  if (!map) {
+    cudaFree(h->d_map[k]);
+    h->d_map[k] = nullptr;
+    h->map_cols[k] = 0;
+    return 0;
+  }
+  if (cols <= 0) return fail(RBIS_ERR_INVALID, "cols must be positive");
+  for (int64_t n = 0; n < h->N; n++)
+    if (map[n] < 0 || map[n] >= cols) return fail(RBIS_ERR_INVALID, "map[%lld] = %d is outside [0, %lld)", (long long)n, map[n], (long long)cols);
+  if (!h->d_map[k]) CUDA_TRY(cudaMalloc(&h->d_map[k], (size_t)h->N * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(h->d_map[k], map, (size_t)h->N * sizeof(int), cudaMemcpyHostToDevice));
+  h->map_cols[k] = cols;
+  return 0;
+}
+
 int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
                          int n_streams, const rbis_stream_t* streams, int mem) {
   if (n_streams > 0 && !streams) return fail(RBIS_ERR_INVALID, "streams is NULL");
@@ -676,7 +706,7 @@ int rbis_batch_ins_step(rbis_batch_t* h, const double* gyro, const double* accel
   CUDA_TRY(cudaMemcpyAsync(h->misc.p + 3 * N, accel, 3 * N * sizeof(double), kind, h->stream));
   rbis_op_t op;
   op.kind = RBIS_OP_IMU; op.stream = 0; op.row = 0; op.utime = utime; op.dt = dt;
-  return launch_fused(h, 1, &op, h->misc.p, 1, 0, nullptr, RBIS_MEM_DEVICE);
+  return launch_fused(h, 1, &op, h->misc.p, 1, 0, nullptr, RBIS_MEM_DEVICE, /*use_maps=*/false);
 }
 
 static int single_meas(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* quat,
@@ -690,7 +720,7 @@ static int single_meas(rbis_batch_t* h, int m, const int32_t* idx, const double*
   st.z = z; st.quat = quat; st.R = R; st.rows = 1;
   rbis_op_t op;
   op.kind = RBIS_OP_MEAS; op.stream = 0; op.row = 0; op.utime = utime; op.dt = 0;
-  return launch_fused(h, 1, &op, nullptr, 0, 1, &st, mem);
+  return launch_fused(h, 1, &op, nullptr, 0, 1, &st, mem, /*use_maps=*/false);
 }
 
 int rbis_batch_indexed_update(rbis_batch_t* h, int m, const int32_t* idx, const double* z, const double* R,

@@ -121,9 +121,11 @@ struct StreamDesc {
   int chunk_start[MAX_CHUNKS];
   int chunk_len[MAX_CHUNKS];
   int chunk_fast[MAX_CHUNKS];  // >= 0: the chunk is the aligned index triple I0..I0+2 (I0 = chunk_fast) -> meas3<I0>
-  const double* z;     // [rows][m][N]
-  const double* quat;  // [rows][4][N]
+  const double* z;     // [rows][m][cols]
+  const double* quat;  // [rows][4][cols]
   const double* R;     // r_mode 0: device copy of m*m column-major; 1: [m][N]
+  const int* map;      // column of z / quat read by filter n (nullptr: column n)
+  long long cols;      // columns of z / quat (N without a map)
 };
 
 struct Op {
@@ -142,7 +144,9 @@ struct KParams {
   const double* q_accel;
   const double* q_gyro_bias;
   const double* q_accel_bias;
-  const double* imu;  // [rows][6][N]
+  const double* imu;  // [rows][6][imu_cols]
+  const int* imu_map; // column of imu read by filter n (nullptr: column n)
+  long long imu_cols;
   double* snap;       // [slots][257][N]
   const Op* ops;
   long long n_ops;
@@ -673,11 +677,11 @@ struct HPRow0 {  // elements (I0, c), (I0+1, c), (I0+2, c) for c = 3k..3k+2 -> n
 
 template <int I0>
 __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& st, int a0, long long row, long long N,
-                                      long long n, const V3& dquat, const V3& chi0) {
+                                      long long n, long long sn, const V3& dquat, const V3& chi0) {
   // issue the measurement loads first; they are consumed after the covariance work
   double z[3], Rdg[3];
 #pragma unroll
-  for (int a = 0; a < 3; a++) z[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * N + n);
+  for (int a = 0; a < 3; a++) z[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * st.cols + sn);
   if (st.r_mode == 1) {
 #pragma unroll
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
@@ -795,8 +799,8 @@ struct GenResult {
 };
 __device__ __noinline__ GenResult meas_general(int M, Cov P, const double* __restrict__ xs, int has_orient, int r_mode,
                                                int m_stream, const int* __restrict__ idxs, const double* __restrict__ zrow,
-                                               const double* __restrict__ Rp, int a0, long long N, long long n, V3 dquat,
-                                               V3 chi0) {
+                                               long long zcols, long long sn, const double* __restrict__ Rp, int a0,
+                                               long long N, long long n, V3 dquat, V3 chi0) {
   double HP[MAX_MEAS][NS], S[MAX_MEAS][MAX_MEAS], Lm[MAX_MEAS][MAX_MEAS], D[MAX_MEAS], r[MAX_MEAS], y[MAX_MEAS];
   int idx[MAX_MEAS];
   for (int a = 0; a < M; a++) idx[a] = idxs[a0 + a];
@@ -852,7 +856,7 @@ __device__ __noinline__ GenResult meas_general(int M, Cov P, const double* __res
       const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
       r[a] = dq - (xi - c0);
     } else {
-      r[a] = __ldg(zrow + (long long)(a0 + a) * N + n) - xi;
+      r[a] = __ldg(zrow + (long long)(a0 + a) * zcols + sn) - xi;
     }
   }
   // y = S^-1 r
@@ -961,15 +965,17 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
 #endif
     return o;
   };
+  const long long imu_n = p.imu_map ? (long long)__ldg(p.imu_map + n) : n;
   Op op_next = load_op(0);
   for (long long oi = 0; oi < p.n_ops; oi++) {
     const Op op = op_next;
     if (oi + 1 < p.n_ops) op_next = load_op(oi + 1);  // fetched one op ahead: its latency hides behind this op
     if (op.kind == 0) {
       // ---- IMU process step ----
-      const double* base = p.imu + op.row * 6 * N + n;
-      const V3 gyro{ldg_early(base), ldg_early(base + N), ldg_early(base + 2 * N)};
-      const V3 acc{ldg_early(base + 3 * N), ldg_early(base + 4 * N), ldg_early(base + 5 * N)};
+      const double* base = p.imu + op.row * 6 * p.imu_cols + imu_n;
+      const long long Ni = p.imu_cols;
+      const V3 gyro{ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
+      const V3 acc{ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
       const double q_gyro = __ldg(p.q_gyro + n), q_accel = __ldg(p.q_accel + n), q_gyro_bias = __ldg(p.q_gyro_bias + n),
                    q_accel_bias = __ldg(p.q_accel_bias + n);
       const double dt = op.dt;
@@ -995,10 +1001,12 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
     } else if (op.kind == 1) {
       // ---- indexed / indexed-plus-orientation measurement ----
       const StreamDesc& st = p.streams[op.stream];
+      const long long sn = st.map ? (long long)__ldg(st.map + n) : n;
       V3 dquat{0, 0, 0};
       if (st.has_orient) {
-        const double* qb = st.quat + op.row * 4 * N + n;
-        const Q4 mq{__ldg(qb), __ldg(qb + N), __ldg(qb + 2 * N), __ldg(qb + 3 * N)};
+        const long long SN = st.cols;
+        const double* qb = st.quat + op.row * 4 * SN + sn;
+        const Q4 mq{__ldg(qb), __ldg(qb + SN), __ldg(qb + 2 * SN), __ldg(qb + 3 * SN)};
         dquat = subtract_quats(mq, {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
       }
       const V3 chi0{s.x[6], s.x[7], s.x[8]};
@@ -1006,20 +1014,20 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         const int a0 = st.chunk_start[ci];
         const int fast = st.chunk_fast[ci];
         switch (fast) {
-          case 0: meas3<0>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 3: meas3<3>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 6: meas3<6>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 9: meas3<9>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 12: meas3<12>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 15: meas3<15>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
-          case 18: meas3<18>(P, s, st, a0, op.row, N, n, dquat, chi0); break;
+          case 0: meas3<0>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 3: meas3<3>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 6: meas3<6>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 9: meas3<9>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 12: meas3<12>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 15: meas3<15>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 18: meas3<18>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           default:
             if constexpr (GENERAL) {
               double xs[NS];
 #pragma unroll
               for (int c = 0; c < NS; c++) xs[c] = s.x[c];
               const GenResult g = meas_general(st.chunk_len[ci], P, xs, st.has_orient, st.r_mode, st.m, st.idx,
-                                               st.z + op.row * st.m * N, st.R, a0, N, n, dquat, chi0);
+                                               st.z + op.row * st.m * st.cols, st.cols, sn, st.R, a0, N, n, dquat, chi0);
 #pragma unroll
               for (int c = 0; c < NS; c++) s.x[c] += g.dx[c];
               s.ll += g.dll;

@@ -495,3 +495,57 @@ def test_launch_groups_do_not_change_results_and_keep_call_order(oracle):
     ref = oracle.run_ensemble(ref["vec"], ref["quat"], ref["cov"], ref["loglik"], ev[cuts[2] - 1][3], (q[0] * 1.5, q[1], q[2], q[3]),
                               st["imu"], oracle_streams(st), ev[cuts[2]:], n_threads=NTHREADS)
     _assert_close((g1[0][:, :64], g1[1][:, :64], g1[2][:, :64]), (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "groups")
+
+
+# ------------------------------------------------------------------------------------------------
+# shared input columns (parameter sweeps over the same data, BASELINE config 4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_column_maps_equal_expanded_inputs_and_oracle(oracle):
+    """N = 12 parameter points x 16 noise realisations: every filter reads one of 16 shared input columns
+    (rbis_batch_set_column_map) and has its own process noise and per-filter diagonal leg-odometry R.  Must be
+    bit-identical to the same run with the columns expanded to per-filter arrays, and match the oracle."""
+    from pronto_b200.batch import make_ops
+
+    C_, G_, T = 16, 12, 60
+    N = C_ * G_
+    sc = scenario(C_, T)
+    st = sc["st"]
+    cmap = (np.arange(N) % C_).astype(np.int32)
+    grid = np.repeat(np.linspace(0.5, 2.0, G_), C_)
+    q = nominal_q()
+    qs = (q[0] * grid, q[1] * grid[::-1].copy(), np.full(N, q[2]), np.full(N, q[3]))
+    r_lego = np.ascontiguousarray(np.tile((synth.NOMINAL["r_vxyz"] ** 2) * grid, (3, 1)))
+    ex = lambda a: np.ascontiguousarray(a[..., cmap])
+    vec, quat, cov = ex(sc["vec"]), ex(sc["quat"]), ex(sc["cov"])
+    ops = make_ops(st["events"])
+    outs = []
+    for mapped in (True, False):
+        with RBISBatch(N) as b:
+            b.set_process_noise(*[np.ascontiguousarray(a) for a in qs])
+            b.set_state(vec, quat, cov)
+            if mapped:
+                b.set_column_map(-1, cmap, C_); b.set_column_map(0, cmap, C_); b.set_column_map(1, cmap, C_)
+                imu, lego, pz, pq = st["imu"], st["legodo"], st["pose_z"], st["pose_q"]
+            else:
+                imu, lego, pz, pq = ex(st["imu"]), ex(st["legodo"]), ex(st["pose_z"]), ex(st["pose_q"])
+            streams = [MeasStream(synth.LEGODO_IDX, lego, r_lego, per_filter_diag=True),
+                       MeasStream(synth.POSE_IDX, pz, st["R_pose"], quat=pq)]
+            b.run_fused(ops, imu=imu, streams=streams)
+            if mapped:  # the one-op entry points ignore the maps ([3][N] inputs)
+                b.ins_step(ex(st["imu"][0, 0:3]), ex(st["imu"][0, 3:6]), 1e-3, utime=10 ** 9)
+                b.set_column_map(-1, None)
+                with pytest.raises(ValueError):
+                    b.run_fused(ops[:1], imu=st["imu"])  # identity again: [rows][6][16] is the wrong shape
+            else:
+                b.ins_step(ex(st["imu"][0, 0:3]), ex(st["imu"][0, 3:6]), 1e-3, utime=10 ** 9)
+            outs.append(b.get_state())
+    for x, y in zip(outs[0][:4], outs[1][:4]):
+        assert np.array_equal(x, y)
+    ev = list(st["events"]) + [(0, 0, 0, 10 ** 9, 1e-3)]
+    ref = oracle.run_ensemble(vec, quat, cov, None, 0, qs, ex(st["imu"]),
+                              [dict(idx=synth.LEGODO_IDX, z=ex(st["legodo"]), R=r_lego, per_filter_diag=True),
+                               dict(idx=synth.POSE_IDX, z=ex(st["pose_z"]), R=st["R_pose"], quat=ex(st["pose_q"]))],
+                              ev, n_threads=NTHREADS)
+    _assert_close(outs[0][:3], (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "column maps")
+    assert _rel_ll(outs[0][3], ref["loglik"]) < STEP_TOL
