@@ -219,6 +219,19 @@ int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* tru
  * the next step. */
 int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int chunk,
                              double* out_chunks, int64_t* n_chunks);
+/* ---- windowed noise-identification likelihood: the per-window term of sampleProcessForward + negLogLikelihood
+ * (state-estimator/src/noise_id/noise_id.cpp:36-40,44-65) for every filter at once.  With the
+ * filters' heads = states rolled forward over one window from the truth, truth_vec [21][N] / truth_quat [4][N] = the
+ * truth at the window ends, and base_cov [441][base_cols] = the covariance the same window accumulates under ZERO
+ * process noise (column base_map[n] for filter n; base_map HOST int32[N], NULL = column n):
+ *   e = head (-) truth (subtractState + quatToChi),  C = cov - base_cov[:, base_map[n]],
+ *   out[n] = -loglike_normalized(e_A, 0, C_AA) = log det C_AA + e_A^T C_AA^-1 e_A     (A = active_idx, host int32[n_active])
+ * Summing out over the windows of one parameter point gives negLogLikelihood.  truth, base_cov, out live as `mem`
+ * says.  Synchronous. */
+int rbis_batch_window_neg_loglik(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, const double* base_cov,
+                                 const int32_t* base_map, int64_t base_cols, int n_active, const int32_t* active_idx,
+                                 double* out, int mem);
+
 /* Stream-ordered completion tickets: record marks "everything enqueued so far", wait blocks the host
  * until that point has completed.  Up to 8 tickets may be outstanding. */
 int rbis_batch_record(rbis_batch_t* h, int32_t* ticket);

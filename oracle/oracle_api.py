@@ -169,3 +169,20 @@ def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events,
     if trace:
         out.update(trace_vec=tr[0], trace_quat=tr[1], trace_cov=tr[2], trace_loglik=tr[3])
     return out
+
+
+def noise_id_neg_loglik(vec, quat, cov, dt, q_gyro, q_accel, n_window, active=(3, 4, 5, 6, 7, 8, 9, 10, 11)):
+    """state-estimator/src/noise_id/noise_id.cpp:9-65 for ONE (q_gyro, q_accel): truth history vec [T1][21],
+    quat [T1][4], cov [T1][441] (column-major RBIM per row) -> (negative log-likelihood, per-window errors [W][21])."""
+    lib = load()
+    lib.orc_noise_id_neg_loglik.restype = C.c_double
+    lib.orc_noise_id_neg_loglik.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    vec, quat, cov = _a(vec), _a(quat), _a(cov)
+    T1 = vec.shape[0]
+    act = np.ascontiguousarray(active, dtype=np.int32)
+    nw = C.c_int64(0)
+    errs = np.zeros((max(1, (T1 - 1) // int(n_window)), 21))
+    v = lib.orc_noise_id_neg_loglik(T1, vec.ctypes.data, quat.ctypes.data, cov.ctypes.data, float(dt), float(q_gyro), float(q_accel),
+                                    int(n_window), len(act), act.ctypes.data, C.byref(nw), errs.ctypes.data)
+    return float(v), errs[:nw.value]

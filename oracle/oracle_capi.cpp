@@ -213,4 +213,25 @@ int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, d
   return calls.load();
 }
 
+// noise identification (state-estimator/src/noise_id/noise_id.cpp:9-65): truth history [T1][21], [T1][4], [T1][441]
+// (row-major over time), one (q_gyro, q_accel) point -> negative log-likelihood over the complete windows.
+// errs/covs (optional): per-window state error [W][21] and active covariance difference [W][n_active^2].
+double orc_noise_id_neg_loglik(int64_t T1, const double* vec, const double* quat, const double* cov, double dt, double q_gyro,
+                               double q_accel, int N_window, int n_active, const int32_t* active, int64_t* n_windows,
+                               double* errs) {
+  std::vector<RBIS> states((size_t)T1);
+  std::vector<RBIM> covs((size_t)T1);
+  for (int64_t t = 0; t < T1; t++) {
+    states[(size_t)t] = makeState(vec + 21 * t, quat + 4 * t);
+    std::memcpy(covs[(size_t)t].m, cov + 441 * t, sizeof(double) * 441);
+  }
+  std::vector<RBIS> errors;
+  std::vector<RBIM> ecovs;
+  sampleProcessForward(states, covs, dt, q_gyro, q_accel, N_window, errors, ecovs);
+  if (n_windows) *n_windows = (int64_t)errors.size();
+  if (errs)
+    for (size_t w = 0; w < errors.size(); w++) std::memcpy(errs + 21 * w, errors[w].vec, sizeof(double) * 21);
+  return negLogLikelihood(errors, ecovs, n_active, active);
+}
+
 }  // extern "C"

@@ -165,3 +165,26 @@ def state_error(est, truth):
     e = est.vec - truth.vec
     e[CHI_:CHI_ + 3] = qlog(qmul(qinv(truth.quat), est.quat))
     return e
+
+
+def noise_id_neg_loglik(states, covs, dt, q_gyro, q_accel, n_window, active=(3, 4, 5, 6, 7, 8, 9, 10, 11)):
+    """state-estimator/src/noise_id/noise_id.cpp:9-65: states = list of State (truth history), covs = list of 21x21.
+    Returns (negative log-likelihood, list of per-window error vectors)."""
+    act = list(active)
+    it, nll, errs = 0, 0.0, []
+    while True:
+        rolled = states[it].copy()
+        start_cov = covs[it].copy()
+        rolled_cov = start_cov.copy()
+        for _ in range(n_window):
+            rolled_cov = ins_update_covariance(q_gyro, q_accel, 0.0, 0.0, rolled, rolled_cov, dt)
+            start_cov = ins_update_covariance(0.0, 0.0, 0.0, 0.0, rolled, start_cov, dt)
+            ins_update_state(states[it].vec[W_:W_ + 3].copy(), states[it].vec[A_:A_ + 3].copy(), dt, rolled)
+            it += 1
+            if it == len(states):
+                return nll, errs
+        e = state_error(rolled, states[it])
+        Cm = (rolled_cov - start_cov)[np.ix_(act, act)]
+        ea = e[act]
+        nll -= -np.log(np.linalg.det(Cm)) - ea @ np.linalg.solve(Cm, ea)  # loglike_normalized [RECALLED], see rbis_oracle.hpp
+        errs.append(e)

@@ -608,4 +608,72 @@ double MavStateEstimator::getMeasurementsLogLikelihood() {
   return history.updateMap.rbegin()->second->loglikelihood;
 }
 
+// ------------------------------------------------------------------------------------------------
+// noise identification, state-estimator/src/noise_id/noise_id.cpp:9-65
+// ------------------------------------------------------------------------------------------------
+void sampleProcessForward(const std::vector<RBIS>& truth_state_history, const std::vector<RBIM>& truth_cov_history, double dt,
+                          double q_gyro, double q_accel, int N_window, std::vector<RBIS>& state_errors, std::vector<RBIM>& covs) {
+  const double q_gyro_bias = 0, q_accel_bias = 0;                       // noise_id.cpp:13-14
+  size_t it = 0;                                                        // truth_state_it / truth_cov_it
+  if (truth_state_history.empty()) return;
+  while (true) {
+    RBIS rolled_state = truth_state_history[it];                        // :19
+    RBIM start_window_cov = truth_cov_history[it];                      // :21
+    RBIM rolled_covariance = start_window_cov;                          // :22
+    for (int ii = 0; ii < N_window; ii++) {
+      insUpdateCovariance(q_gyro, q_accel, q_gyro_bias, q_accel_bias, rolled_state, rolled_covariance, dt);  // :24
+      insUpdateCovariance(0, 0, 0, 0, rolled_state, start_window_cov, dt);                                   // :25
+      insUpdateState(truth_state_history[it].angularVelocity(), truth_state_history[it].acceleration(), dt, rolled_state);  // :26
+      rolled_state.utime = truth_state_history[it].utime;               // :27
+      it++;                                                             // :31-32
+      if (it == truth_state_history.size()) return;                     // :33-34
+    }
+    rolled_state.subtractState(truth_state_history[it]);                // :37
+    rolled_state.quatToChi();                                           // :38
+    state_errors.push_back(rolled_state);                               // :39
+    RBIM d;
+    for (int k = 0; k < N * N; k++) d.m[k] = rolled_covariance.m[k] - start_window_cov.m[k];
+    covs.push_back(d);                                                  // :40
+  }
+}
+
+double loglike_normalized(int n, const double* x, const double* mu, const double* sigma) {
+  // LDL^T without pivoting of the symmetric positive definite sigma; det = prod d, solve by substitution
+  std::vector<double> L((size_t)n * n, 0.0), D((size_t)n), diff((size_t)n), y((size_t)n);
+  for (int i = 0; i < n; i++) diff[(size_t)i] = mu[i] - x[i];
+  double logdet = 0;
+  for (int k = 0; k < n; k++) {
+    double d = sigma[k + n * k];
+    for (int p = 0; p < k; p++) d -= L[(size_t)(k + n * p)] * L[(size_t)(k + n * p)] * D[(size_t)p];
+    D[(size_t)k] = d;
+    logdet += std::log(d);
+    for (int i = k + 1; i < n; i++) {
+      double v = sigma[i + n * k];
+      for (int p = 0; p < k; p++) v -= L[(size_t)(i + n * p)] * L[(size_t)(k + n * p)] * D[(size_t)p];
+      L[(size_t)(i + n * k)] = v / d;
+    }
+  }
+  double quad = 0;
+  for (int i = 0; i < n; i++) {
+    double v = diff[(size_t)i];
+    for (int k = 0; k < i; k++) v -= L[(size_t)(i + n * k)] * y[(size_t)k];
+    y[(size_t)i] = v;
+    quad += v * v / D[(size_t)i];
+  }
+  return -logdet - quad;
+}
+
+double negLogLikelihood(const std::vector<RBIS>& state_errors, const std::vector<RBIM>& covs, int n_active, const int32_t* active_inds) {
+  double neg_likelihood = 0;                                            // noise_id.cpp:49
+  std::vector<double> cov_active((size_t)n_active * n_active), error_active((size_t)n_active), zero((size_t)n_active, 0.0);
+  for (size_t w = 0; w < state_errors.size(); w++) {
+    for (int a = 0; a < n_active; a++) {
+      error_active[(size_t)a] = state_errors[w].vec[active_inds[a]];
+      for (int b = 0; b < n_active; b++) cov_active[(size_t)(a + n_active * b)] = covs[w](active_inds[a], active_inds[b]);
+    }
+    neg_likelihood -= loglike_normalized(n_active, error_active.data(), zero.data(), cov_active.data());  // :58-60
+  }
+  return neg_likelihood;
+}
+
 }  // namespace rbis_oracle

@@ -83,6 +83,7 @@ struct RBIS {
   const double* angularVelocity() const { return vec + angular_velocity_ind; }
   const double* velocity() const { return vec + velocity_ind; }
   const double* chi() const { return vec + chi_ind; }
+  const double* acceleration() const { return vec + acceleration_ind; }
   void chiToQuat();
   void quatToChi();
   void addState(const RBIS& d);
@@ -105,6 +106,17 @@ double indexedPlusOrientationMeasurement(int m, const double* z, const Quat& qua
                                          RBIS& dstate, RBIM& dcov);
 void rbisApplyDelta(const RBIS& prior_state, const RBIM& prior_cov, const RBIS& dstate, const RBIM& dcov,
                     RBIS& posterior_state, RBIM& posterior_cov);
+
+// ---- IMU-noise identification, state-estimator/src/noise_id/noise_id.cpp:9-65 ("next" row 2 of SURVEY.md 8f) ----
+// sampleProcessForward: windows of N_window IMU steps rolled forward from the truth history with TWO covariance
+// propagations per step (the given noise, and zero noise from the same start) -- state_errors / covs per complete window.
+void sampleProcessForward(const std::vector<RBIS>& truth_state_history, const std::vector<RBIM>& truth_cov_history, double dt,
+                          double q_gyro, double q_accel, int N_window, std::vector<RBIS>& state_errors, std::vector<RBIM>& covs);
+// eigen_utils::loglike_normalized [RECALLED]: -log det(sigma) - (mu - x)^T sigma^-1 (mu - x)  (no 1/2, no 2 pi; the same
+// form MSE/rbis.cpp:142 writes inline)
+double loglike_normalized(int n, const double* x, const double* mu, const double* sigma /* n x n column-major */);
+// negLogLikelihood over the active index set (noise_id.cpp:44-65)
+double negLogLikelihood(const std::vector<RBIS>& state_errors, const std::vector<RBIM>& covs, int n_active, const int32_t* active_inds);
 
 // ---- update objects: rbis_update_interface.hpp:8-120 ----
 class RBISUpdateInterface {

@@ -797,6 +797,51 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
   return 0;
 }
 
+int rbis_batch_window_neg_loglik(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, const double* base_cov,
+                                 const int32_t* base_map, int64_t base_cols, int n_active, const int32_t* active_idx,
+                                 double* out, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!truth_vec || !truth_quat || !base_cov || !active_idx || !out) return fail(RBIS_ERR_INVALID, "null argument");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (n_active < 1 || n_active > RBIS_NUM_STATES) return fail(RBIS_ERR_INVALID, "n_active out of range");
+  for (int a = 0; a < n_active; a++)
+    if (active_idx[a] < 0 || active_idx[a] >= RBIS_NUM_STATES) return fail(RBIS_ERR_INVALID, "active index out of range");
+  const size_t N = (size_t)h->N;
+  if (!base_map) base_cols = (int64_t)N;
+  if (base_cols <= 0) return fail(RBIS_ERR_INVALID, "base_cols must be positive");
+  if (base_map)
+    for (size_t n = 0; n < N; n++)
+      if (base_map[n] < 0 || base_map[n] >= base_cols) return fail(RBIS_ERR_INVALID, "base_map entry out of range");
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  // scratch (doubles): truth 25N + base 441*cols + out N + ints (map N + active 21, packed into doubles)
+  const size_t n_truth = mem == RBIS_MEM_HOST ? 25 * N : 0, n_base = mem == RBIS_MEM_HOST ? 441 * (size_t)base_cols : 0;
+  const size_t n_int = (N + RBIS_NUM_STATES + 1) / 2 + 1;
+  if (h->misc.ensure(n_truth + n_base + N + n_int)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  double* d_truth = h->misc.p;
+  double* d_base = d_truth + n_truth;
+  double* d_out = d_base + n_base;
+  int* d_int = reinterpret_cast<int*>(d_out + N);
+  const double *tv = truth_vec, *tq = truth_quat, *bc = base_cov;
+  if (mem == RBIS_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(d_truth, truth_vec, 21 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_truth + 21 * N, truth_quat, 4 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_base, base_cov, n_base * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    tv = d_truth; tq = d_truth + 21 * N; bc = d_base;
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_int, active_idx, (size_t)n_active * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (base_map) CUDA_TRY(cudaMemcpyAsync(d_int + RBIS_NUM_STATES, base_map, N * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  double* o = mem == RBIS_MEM_DEVICE ? out : d_out;
+  rbisk::window_nll_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(
+      h->vec, h->quat, h->P, tv, tq, bc, base_map ? d_int + RBIS_NUM_STATES : nullptr, (long long)base_cols, n_active,
+      d_int, (long long)N, o);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out, d_out, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int rbis_batch_record(rbis_batch_t* h, int32_t* ticket) {
   if (!h || !ticket) return fail(RBIS_ERR_INVALID, "null handle or ticket");
   if (int rc = use_device(h)) return rc;

@@ -100,6 +100,48 @@ __global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ 
   if (t >= 48 && t < NSTAT) out_chunks[(long long)blockIdx.x * NSTAT + t] = 0.0;
 }
 
+// ---- windowed noise-identification likelihood (SE/noise_id/noise_id.cpp:36-40,44-65) ----
+// One lane per filter: e = head (-) truth (subtractState + quatToChi), C = cov - base_cov[:, map[n]] (the covariance the
+// same window accumulates under zero process noise), out = log det C_AA + e_A^T C_AA^-1 e_A = -loglike_normalized(e_A, 0, C_AA).
+__global__ void window_nll_kernel(const double* __restrict__ vec, const double* __restrict__ quat, const double* __restrict__ P,
+                                  const double* __restrict__ tvec, const double* __restrict__ tquat,
+                                  const double* __restrict__ base_cov, const int* __restrict__ base_map, long long base_cols,
+                                  int n_active, const int* __restrict__ active, long long N, double* __restrict__ out) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double e[NS];
+  for (int i = 0; i < NS; i++) e[i] = vec[(long long)i * N + n] - tvec[(long long)i * N + n];
+  const Q4 q{quat[n], quat[N + n], quat[2 * N + n], quat[3 * N + n]};
+  const Q4 tq{tquat[n], tquat[N + n], tquat[2 * N + n], tquat[3 * N + n]};
+  const V3 dchi = subtract_quats(q, tq);
+  // quatToChi after subtractState: chi = Log(truth^-1 * est); the vec chi difference is dropped by the reference only
+  // if the fold happened -- subtractState subtracts vec (chi included) and quatToChi OVERWRITES chi (eigen_utils)
+  e[6] = dchi.x; e[7] = dchi.y; e[8] = dchi.z;
+  const long long bc = base_map ? (long long)base_map[n] : n;
+  double L[NS][NS], D[NS], y[NS];
+  double logdet = 0, quad = 0;
+  for (int k = 0; k < n_active; k++) {
+    const int ik = active[k];
+    double d = P[(long long)slot(ik, ik) * N + n] - base_cov[(long long)(ik + NS * ik) * base_cols + bc];
+    for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p] * D[p];
+    D[k] = d;
+    logdet += log(d);
+    for (int i = k + 1; i < n_active; i++) {
+      const int ii = active[i];
+      double v = P[(long long)slot(ii, ik) * N + n] - base_cov[(long long)(ii + NS * ik) * base_cols + bc];
+      for (int p = 0; p < k; p++) v -= L[i][p] * L[k][p] * D[p];
+      L[i][k] = v / d;
+    }
+  }
+  for (int i = 0; i < n_active; i++) {
+    double v = -e[active[i]];  // diff = mu - x with mu = 0
+    for (int k = 0; k < i; k++) v -= L[i][k] * y[k];
+    y[i] = v;
+    quad += v * v / D[i];
+  }
+  out[n] = logdet + quad;
+}
+
 // ---- FP64 roofline denominators ----
 constexpr int DFMA_CHAINS = 8;
 constexpr int DFMA_UNROLL = 32;
