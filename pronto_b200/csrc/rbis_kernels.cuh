@@ -45,6 +45,9 @@
 #ifndef RBIS_EARLY_LOADS
 #define RBIS_EARLY_LOADS 1
 #endif
+#ifndef RBIS_ZV_SINGLE_CHAIN
+#define RBIS_ZV_SINGLE_CHAIN 0
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -443,10 +446,14 @@ __device__ __forceinline__ V3 zp(const Lin& L, const V3& pv, const V3& pc, const
 }
 // rows v:  z = P[v,c] - wd x P[v,c] + gd x P[chi,c] - vd x P[bg,c] - dt P[ba,c]
 __device__ __forceinline__ V3 zv(const Lin& L, const V3& pv, const V3& pc, const V3& pg, const V3& pa) {
+#if RBIS_ZV_SINGLE_CHAIN
+  return sub_cross(add_cross(sub_cross(axpy(-L.dt, pa, pv), L.wd, pv), L.gd, pc), L.vd, pg);  // 7 dependent FMAs, no join
+#else
   const V3 a = sub_cross(pv, L.wd, pv);
   const V3 b = add_cross(axpy(-L.dt, pa, {0.0, 0.0, 0.0}), L.gd, pc);  // second chain, joined at the end
   const V3 c = sub_cross(a, L.vd, pg);
   return {c.x + b.x, c.y + b.y, c.z + b.z};
+#endif
 }
 // rows chi:  z = P[chi,c] - wd x P[chi,c] - dt P[bg,c]
 __device__ __forceinline__ V3 zc(const Lin& L, const V3& pc, const V3& pg) { return sub_cross(axpy(-L.dt, pg, pc), L.wd, pc); }
