@@ -12,7 +12,9 @@
 #ifndef RBIS_BATCH_HPP_
 #define RBIS_BATCH_HPP_
 
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -339,6 +341,93 @@ class MavStateEstimator {
   int64_t next_id_ = 0, newest_ = INT64_MIN, launches_ = 0;
   std::array<double, 4> cur_q_{};
   bool have_cur_q_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Leg-odometry measurement formation for an ensemble: MavStateEst::LegOdoCommon
+// (motion_estimate/src/mav_est_legodo/rbis_legodo_common.{hpp,cpp}), the step
+// immediately before RBISIndexedMeasurement.  Pure input shaping (no filter math): delta pose ->
+// body velocity, index set and R by mode, "uncertain" R while a foot breaks contact.  Per-filter
+// arrays are [k][N]; the status flags are shared by the ensemble (one robot, N replicas).
+// ------------------------------------------------------------------------------------------------
+class LegOdoCommon {
+ public:
+  typedef enum { MODE_LIN_RATE, MODE_ROT_RATE, MODE_LIN_AND_ROT_RATE, MODE_POSITION_AND_LIN_RATE } LegOdoCommonMode;  // rbis_legodo_common.hpp:15-17
+  LegOdoCommonMode mode_;
+  double R_legodo_xyz_, R_legodo_vxyz_, R_legodo_vang_, R_legodo_vxyz_uncertain_, R_legodo_vang_uncertain_;
+
+  // the config keys state_estimator.legodo.{mode,r_xyz,r_vxyz,r_vang,r_vxyz_uncertain,r_vang_uncertain} (rbis_legodo_common.cpp:9-33)
+  LegOdoCommon(LegOdoCommonMode mode, double r_xyz, double r_vxyz, double r_vang, double r_vxyz_uncertain, double r_vang_uncertain)
+      : mode_(mode), R_legodo_xyz_(r_xyz), R_legodo_vxyz_(r_vxyz), R_legodo_vang_(r_vang), R_legodo_vxyz_uncertain_(r_vxyz_uncertain),
+        R_legodo_vang_uncertain_(r_vang_uncertain) {}
+
+  // rbis_legodo_common.cpp:35-88.  cov_legodo: m x m column-major (diagonal).
+  void getCovariance(LegOdoCommonMode mode_current, bool delta_certain, std::vector<double>& cov_legodo, std::vector<int32_t>& z_indices) const {
+    const double vxyz = delta_certain ? R_legodo_vxyz_ : R_legodo_vxyz_uncertain_;
+    const double vang = delta_certain ? R_legodo_vang_ : R_legodo_vang_uncertain_;
+    std::vector<double> R;
+    auto sq = [](double v) { return v * v; };
+    if (mode_current == MODE_LIN_AND_ROT_RATE) {
+      R = {sq(vxyz), sq(vxyz), sq(vxyz), sq(vang), sq(vang), sq(vang)};
+      z_indices = {RBIS::velocity_ind, RBIS::velocity_ind + 1, RBIS::velocity_ind + 2, RBIS::angular_velocity_ind,
+                   RBIS::angular_velocity_ind + 1, RBIS::angular_velocity_ind + 2};
+    } else if (mode_current == MODE_LIN_RATE) {
+      R = {sq(vxyz), sq(vxyz), sq(vxyz)};
+      z_indices = {RBIS::velocity_ind, RBIS::velocity_ind + 1, RBIS::velocity_ind + 2};
+    } else if (mode_current == MODE_POSITION_AND_LIN_RATE) {
+      R = {sq(R_legodo_xyz_), sq(R_legodo_xyz_), sq(R_legodo_xyz_), sq(vxyz), sq(vxyz), sq(vxyz)};
+      z_indices = {RBIS::position_ind, RBIS::position_ind + 1, RBIS::position_ind + 2, RBIS::velocity_ind, RBIS::velocity_ind + 1,
+                   RBIS::velocity_ind + 2};
+    } else {
+      throw Error(RBIS_ERR_INVALID, "LegOdoCommon: mode not supported");  // the reference leaves the vectors unsized here
+    }
+    const size_t m = R.size();
+    cov_legodo.assign(m * m, 0.0);
+    for (size_t a = 0; a < m; a++) cov_legodo[a + m * a] = R[a];
+  }
+
+  // libbot bot_quat_to_roll_pitch_yaw (q = w,x,y,z)
+  static void quatToRollPitchYaw(const double q[4], double rpy[3]) {
+    rpy[0] = std::atan2(2 * (q[0] * q[1] + q[2] * q[3]), 1 - 2 * (q[1] * q[1] + q[2] * q[2]));
+    rpy[1] = std::asin(2 * (q[0] * q[2] - q[3] * q[1]));
+    rpy[2] = std::atan2(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] * q[2] + q[3] * q[3]));
+  }
+
+  // rbis_legodo_common.cpp:110-170.  odo_position_xyz [3][N]: pelvis position; odo_delta_xyz [3][N] and
+  // odo_delta_quat [4][N]: pose increment since prev_utime.  The velocity is delta / elapsed time
+  // (pronto_conversions_lcm.hpp:38-87 getDeltaAsVelocity); the caller owns the returned update (or hands it to addUpdate).
+  RBISUpdateInterface* createMeasurement(const std::vector<double>& odo_position_xyz, const std::vector<double>& odo_delta_xyz,
+                                         const std::vector<double>& odo_delta_quat, int64_t n_filters, int64_t utime, int64_t prev_utime,
+                                         int odo_position_status, float odo_delta_status) const {
+    const size_t N = (size_t)n_filters;
+    const double elapsed_time = (double)(utime - prev_utime) * 1E-6;
+    LegOdoCommonMode mode_current = mode_;
+    if (mode_current == MODE_POSITION_AND_LIN_RATE && !odo_position_status) mode_current = MODE_LIN_RATE;  // :117-121
+    const bool delta_certain = odo_delta_status < 0.5f;                                                  // :123-128
+    std::vector<double> cov_legodo;
+    std::vector<int32_t> z_indices;
+    getCovariance(mode_current, delta_certain, cov_legodo, z_indices);
+    std::vector<double> vel(3 * N);
+    for (size_t k = 0; k < 3 * N; k++) vel[k] = odo_delta_xyz[k] / elapsed_time;
+    std::vector<double> z;
+    if (mode_current == MODE_LIN_AND_ROT_RATE) {   // :135-153
+      z.resize(6 * N);
+      std::copy(vel.begin(), vel.end(), z.begin());
+      for (size_t n = 0; n < N; n++) {
+        const double q[4] = {odo_delta_quat[n], odo_delta_quat[N + n], odo_delta_quat[2 * N + n], odo_delta_quat[3 * N + n]};
+        double rpy[3];
+        quatToRollPitchYaw(q, rpy);
+        for (int k = 0; k < 3; k++) z[(3 + (size_t)k) * N + n] = rpy[k] / elapsed_time;
+      }
+    } else if (mode_current == MODE_LIN_RATE) {    // :154-157
+      z = vel;
+    } else {                                       // MODE_POSITION_AND_LIN_RATE, :158-165
+      z.resize(6 * N);
+      std::copy(odo_position_xyz.begin(), odo_position_xyz.begin() + (long)(3 * N), z.begin());
+      std::copy(vel.begin(), vel.end(), z.begin() + (long)(3 * N));
+    }
+    return new RBISIndexedMeasurement(z_indices, z, cov_legodo, RBISUpdateInterface::legodo, utime);
+  }
 };
 
 }  // namespace batch

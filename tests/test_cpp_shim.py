@@ -102,3 +102,40 @@ def test_shim_replay_matches_oracle_history(shim_exe, tmp_path):
     assert e["vec"] < 1e-9 and e["quat"] < 1e-9 and e["cov"] < 1e-9, e
     assert np.max(np.abs(gll - ref["loglik"]) / np.maximum(1.0, np.abs(ref["loglik"]))) < 1e-9
     assert dropped == 0 and launches == len(arrivals)  # one fused launch per addUpdate(roll_forward=true)
+
+
+def test_legodo_measurement_formation(rbis_lib, tmp_path):
+    """MavStateEst::batch::LegOdoCommon against the formulas of rbis_legodo_common.cpp:35-170 /
+    pronto_conversions_lcm.hpp:38-87 (velocity = delta / elapsed; index set and R by mode; uncertain R when
+    odo_delta_status >= 0.5; fall back to lin_rate without a valid position).  CPU only: no filter math."""
+    exe = os.path.join(BUILD, "legodo_check")
+    os.makedirs(BUILD, exist_ok=True)
+    libdir = os.path.join(ROOT, "pronto_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-o", exe, os.path.join(ROOT, "tests", "cpp", "legodo_check.cpp"),
+                           f"-L{libdir}", "-lrbis_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    rows = {}
+    for line in out:
+        tag, rest = line.split(" ", 1)
+        f = dict(kv.split("=", 1) for kv in rest.split(" "))
+        rows[tag] = dict(m=int(f["m"]), idx=[int(v) for v in f["idx"].split(",") if v], R=[float(v) for v in f["Rdiag"].split(",") if v],
+                         off=float(f["offdiag"]), z=np.array([float(v) for v in f["z"].split(",") if v]), utime=int(f["utime"]),
+                         sensor=int(f["sensor"]))
+    dxyz = np.array([[0.002, 0.004], [-0.001, 0.003], [0.0005, 0.0015]])
+    pos = np.array([[1.0, 2], [3, 4], [5, 6]])
+    v2 = (dxyz / 0.002).reshape(-1)
+    r = rows["lin_certain"]
+    assert r["idx"] == [3, 4, 5] and r["R"] == [0.1 ** 2] * 3 and r["off"] == 0 and r["sensor"] == 11 and r["utime"] == 1002000
+    assert np.allclose(r["z"], v2, rtol=1e-15)
+    assert rows["lin_uncertain"]["R"] == [0.5 ** 2] * 3 and np.array_equal(rows["lin_uncertain"]["z"], r["z"])
+    p = rows["posvel"]
+    assert p["idx"] == [9, 10, 11, 3, 4, 5] and p["R"] == [0.01 ** 2] * 3 + [0.1 ** 2] * 3
+    assert np.allclose(p["z"], np.concatenate([pos.reshape(-1), v2]), rtol=1e-15)
+    assert rows["posvel_nopos"]["idx"] == [3, 4, 5] and np.array_equal(rows["posvel_nopos"]["z"], r["z"])
+    lr = rows["linrot"]
+    assert lr["idx"] == [3, 4, 5, 0, 1, 2] and lr["R"] == [0.5 ** 2] * 3 + [0.9 ** 2] * 3
+    q = np.array([[0.99999, 0.99998], [0.002, -0.001], [0.001, 0.003], [0.004, 0.002]])
+    rpy = np.stack([np.arctan2(2 * (q[0] * q[1] + q[2] * q[3]), 1 - 2 * (q[1] ** 2 + q[2] ** 2)),
+                    np.arcsin(2 * (q[0] * q[2] - q[3] * q[1])),
+                    np.arctan2(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] ** 2 + q[3] ** 2))])
+    assert np.allclose(lr["z"], np.concatenate([(dxyz / 0.004).reshape(-1), (rpy / 0.004).reshape(-1)]), rtol=1e-14)
