@@ -297,6 +297,32 @@ def run_reference(args):
     emit(line)
 
 
+def bind_to_gpu_numa_node(local, rank):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, BEFORE any pinned buffer is
+    allocated: first-touch then places the staging memory on the GPU's NUMA node, which is what decides the
+    host->device rate once several ranks copy at the same time."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                idx = int(ids[local])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"[rank {rank}] bound to {len(cpus)} CPUs local to GPU {idx}")
+    except Exception as e:  # affinity is an optimisation only
+        log(f"[rank {rank}] no NUMA binding ({type(e).__name__}: {e})")
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -316,6 +342,7 @@ def run_b200(args):
         ge.build_cuda()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(local, rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, Tc, K, W = args.filters, args.chunk_steps, args.steps, args.warmup
