@@ -49,6 +49,15 @@
 #ifndef RBIS_ZV_SINGLE_CHAIN
 #define RBIS_ZV_SINGLE_CHAIN 0
 #endif
+#ifndef RBIS_OP_BARRIER
+#define RBIS_OP_BARRIER 0
+#endif
+#ifndef RBIS_LATE_LOADS
+#define RBIS_LATE_LOADS 0
+#endif
+#ifndef RBIS_PARK_STATE
+#define RBIS_PARK_STATE 0
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -75,6 +84,11 @@ __host__ __device__ constexpr int col_of_slot(int s) { int j = 0; while ((j + 1)
 __host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s) * (col_of_slot(s) + 1) / 2; }
 #ifndef RBIS_PLACEMENT
 #define RBIS_PLACEMENT 1
+#endif
+#ifdef RBIS_PARK_STATE
+#define RBIS_PARK_STATE_SLOTS RBIS_PARK_STATE
+#else
+#define RBIS_PARK_STATE_SLOTS 0
 #endif
 // Which memory holds slot (i <= j):
 //   placement 0: the 15x15 active part in tensor memory, the omega/a-coupled part in shared memory;
@@ -115,7 +129,7 @@ __host__ __device__ constexpr int sm_index(int i, int j) { return kPlace.idx[slo
 
 constexpr int N_TM = kPlace.n_tm;   // slots in tensor memory
 constexpr int N_SM = kPlace.n_sm;   // slots in shared memory
-static_assert(N_TM <= 128, "a thread owns 128 doubles of tensor memory");
+static_assert(N_TM + 10 * RBIS_PARK_STATE_SLOTS <= 128, "a thread owns 128 doubles of tensor memory");
 static_assert(N_SM * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
 constexpr int SMEM_BYTES = N_SM * TPB * 8;
 
@@ -473,8 +487,14 @@ template <int C> using FetchEv = ColRows<C, 3, 6, 15, 18>;   // rows v, chi, bg,
 template <int C> using FetchEc = ColRows<C, 6, 15>;          // rows chi, bg
 template <int C> using FetchAll = ColRows<C, 3, 6, 9, 15, 18>;
 
-__device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyro, double q_accel, double q_gyro_bias,
-                                              double q_accel_bias) {
+// after_passive() returns the four process-noise values and before_ev() is called between E_p and E_v: the kernel
+// issues the loads of the noise parameters / of the IMU sample there, so that those registers are not held
+// through the phases with the highest pressure (see RBIS_LATE_LOADS).
+struct QNoise {
+  double q_gyro, q_accel, q_gyro_bias, q_accel_bias;
+};
+template <class AfterPassive, class BeforeEv>
+__device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive&& after_passive, BeforeEv&& before_ev) {
   const double dt = L.dt;
   // ---------------- passive columns omega (0..2), a (12..14): all three congruences in one pass ----------------
   for_columns<FetchAll>(P, ColList<0, 1, 2, 12, 13, 14>{}, [&](auto cc, const double* d, auto) {
@@ -485,6 +505,8 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
     P.setcol3<6, c>(zc(L, pc, pg));
     RBIS_SCHED_FENCE();
   });
+  const QNoise qn = after_passive();
+  const double q_gyro = qn.q_gyro, q_accel = qn.q_accel, q_gyro_bias = qn.q_gyro_bias, q_accel_bias = qn.q_accel_bias;
   // ---------------- E_p on the active block: block row p (9..11), sources v (3..5), chi (6..8) ----------------
   // column order p, v, chi, bg, ba.  Stores: (p,v) after the v columns, (p,chi) after the chi columns,
   // (p,p) after that, (p,c) per column for bg/ba -- none is read by a later fetch of this phase.
@@ -516,6 +538,7 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, double q_gyr
     });
   }
   tm_wait_st();
+  before_ev();
   // ---------------- E_v: block row v (3..5), sources v, chi, bg (15..17), ba (18..20) ----------------
   // column order v, chi, bg, ba, p.  P'[v,v] = Zv + Zv skew(wd) - Zc skew(gd) + Zg skew(vd) - dt Za + Qd[v,v]
   // is accumulated block by block; each Z block is stored as soon as it is complete.
@@ -977,15 +1000,28 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   Op op_next = load_op(0);
   for (long long oi = 0; oi < p.n_ops; oi++) {
     const Op op = op_next;
+#if RBIS_OP_BARRIER
+    __syncthreads();  // keeps the CTA's warps on the same op (instruction-cache locality)
+#endif
     if (oi + 1 < p.n_ops) op_next = load_op(oi + 1);  // fetched one op ahead: its latency hides behind this op
     if (op.kind == 0) {
       // ---- IMU process step ----
       const double* base = p.imu + op.row * 6 * p.imu_cols + imu_n;
       const long long Ni = p.imu_cols;
-      const V3 gyro{ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
-      const V3 acc{ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
-      const double q_gyro = __ldg(p.q_gyro + n), q_accel = __ldg(p.q_accel + n), q_gyro_bias = __ldg(p.q_gyro_bias + n),
-                   q_accel_bias = __ldg(p.q_accel_bias + n);
+      V3 gyro, acc;
+      QNoise qn;
+      auto load_q = [&]() {
+        qn.q_gyro = ldg_early(p.q_gyro + n); qn.q_accel = ldg_early(p.q_accel + n);
+        qn.q_gyro_bias = ldg_early(p.q_gyro_bias + n); qn.q_accel_bias = ldg_early(p.q_accel_bias + n);
+      };
+      auto load_inputs = [&]() {
+        gyro = {ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
+        acc = {ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
+      };
+#if !RBIS_LATE_LOADS
+      load_inputs();
+      load_q();
+#endif
       const double dt = op.dt;
       const Q4 q{s.qw, s.qx, s.qy, s.qz};
       const V3 gb = qrot(qinv(q), V3{0.0, 0.0, -p.g_val});
@@ -1004,7 +1040,36 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         L.Rd[3] = (txy + twz) * dt;       L.Rd[4] = (1 - (txx + tzz)) * dt; L.Rd[5] = (tyz - twx) * dt;
         L.Rd[6] = (txz - twy) * dt;       L.Rd[7] = (tyz + twx) * dt;       L.Rd[8] = (1 - (txx + tyy)) * dt;
       }
-      cov_propagate(P, L, q_gyro, q_accel, q_gyro_bias, q_accel_bias);
+#if RBIS_PARK_STATE
+      // x[9..11], x[15..20] and the log-likelihood are not needed by the covariance step: parked in this thread's ten
+      // spare tensor-memory slots, their 20 registers go to the column pipelines
+      static_for<3>([&](auto k) { tm_st2(P.tm + 2 * (N_TM + k), s.x[9 + k]); });
+      static_for<6>([&](auto k) { tm_st2(P.tm + 2 * (N_TM + 3 + k), s.x[15 + k]); });
+      tm_st2(P.tm + 2 * (N_TM + 9), s.ll);
+#endif
+      cov_propagate(P, L,
+                    [&]() {
+#if RBIS_LATE_LOADS
+                      load_q();
+#endif
+                      return qn;
+                    },
+                    [&]() {
+#if RBIS_LATE_LOADS
+                      load_inputs();
+#endif
+                    });
+#if RBIS_PARK_STATE
+      {
+        Buf<10> pk;
+        static_for<10>([&](auto k) { tm_ld2(P.tm + 2 * (N_TM + k), pk.lo[k], pk.hi[k]); });
+        tm_wait_ld();
+        static_for<10>([&](auto k) { pk.d[k] = tm_settle(pk.lo[k], pk.hi[k]); });
+        static_for<3>([&](auto k) { s.x[9 + k] = pk.d[k]; });
+        static_for<6>([&](auto k) { s.x[15 + k] = pk.d[3 + k]; });
+        s.ll = pk.d[9];
+      }
+#endif
       state_propagate(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
     } else if (op.kind == 1) {
       // ---- indexed / indexed-plus-orientation measurement ----
