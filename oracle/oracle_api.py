@@ -52,6 +52,53 @@ def load():
     return _lib
 
 
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "librbis_ref.so")
+REF_ROOT = "/root/reference"
+_ref_lib = None
+
+
+def build_ref(force=False):
+    """oracle/_ref/librbis_ref.so = the reference's OWN rbis.cpp compiled unmodified against oracle/ref_shim/ (see
+    oracle/Makefile).  Needs the reference tree; returns None where neither the tree nor a prebuilt library exists."""
+    if os.path.isdir(os.path.join(REF_ROOT, "state-estimator")) and (force or not os.path.exists(REF_LIB_PATH)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
+
+
+class reference:
+    """Context manager: inside it the single-update functions of this module (linearization, ins_update_state,
+    ins_update_covariance, measurement_update, set_constants) run the REFERENCE's compiled rbis.cpp instead of the
+    oracle's restatement."""
+
+    def __enter__(self):
+        global _lib, _ref_lib
+        if _ref_lib is None:
+            path = build_ref()
+            if path is None:
+                raise FileNotFoundError("oracle/_ref/librbis_ref.so is not built and /root/reference is not mounted")
+            lib = C.CDLL(path)
+            vp, d = C.c_void_p, C.c_double
+            lib.orc_set_constants.argtypes = [d, d, C.c_int]
+            lib.orc_linearization.argtypes = [vp, vp, vp]
+            lib.orc_ins_update_state.argtypes = [vp, vp, d, vp, vp]
+            lib.orc_ins_update_covariance.argtypes = [d, d, d, d, vp, vp, vp, d]
+            lib.orc_indexed_measurement.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+            lib.orc_indexed_measurement.restype = d
+            lib.orc_apply_delta.argtypes = [vp] * 9
+            lib.orc_run_ensemble.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int,
+                                             C.POINTER(_Stream), C.c_int64, vp, C.c_int64, vp, vp, vp, vp]
+            lib.orc_run_ensemble.restype = C.c_int64
+            _ref_lib = lib
+        load()
+        self._saved = _lib
+        _lib = _ref_lib
+        return self
+
+    def __exit__(self, *a):
+        global _lib
+        _lib = self._saved
+
+
 def _a(x, n=None):
     x = np.ascontiguousarray(x, dtype=np.float64)
     if n is not None:

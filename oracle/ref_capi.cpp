@@ -1,0 +1,190 @@
+// ref_capi.cpp -- extern "C" face of oracle/_ref/librbis_ref.so: the REFERENCE's own
+// state-estimator/src/mav_state_est/rbis.cpp, compiled UNMODIFIED from /root/reference against the stand-in
+// headers of oracle/ref_shim/ (Eigen, eigen_utils, LCM and libbot are not installed).  TEST INFRASTRUCTURE:
+// it pins the oracle's restatement of rbis.cpp:12-227 line by line (tests/test_ref_pins_oracle.py).  What it
+// does NOT pin is eigen_utils itself (RigidBodyState algebra, g_vec, chiToQuat tolerance): those semantics
+// are the same [RECALLED] ones in both, see oracle/ref_shim/eigen_utils/eigen_utils.hpp.
+// Same symbol names and signatures as oracle_capi.cpp's single-update functions.
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "mav_state_est.hpp"  // the reference's headers, found with -I /root/reference/state-estimator/src/mav_state_est
+
+extern "C" int64_t rbis_ref_shim_history_span = 10000000;  // what the BotParam stand-in returns (ref_shim/bot_param)
+
+using namespace MavStateEst;
+
+namespace {
+RBIS makeState(const double* vec, const double* quat) {
+  RBIS::VectorNd v = Eigen::Map<const RBIS::VectorNd>(vec);
+  return RBIS(v, Eigen::Quaterniond(quat[0], quat[1], quat[2], quat[3]));
+}
+void putState(const RBIS& s, double* vec, double* quat) {
+  for (int i = 0; i < 21; i++) vec[i] = s.vec(i);
+  quat[0] = s.quat.w(); quat[1] = s.quat.x(); quat[2] = s.quat.y(); quat[3] = s.quat.z();
+}
+RBIM getCov(const double* cov) { return RBIM(Eigen::Map<const RBIM>(cov)); }
+void putCov(const RBIM& P, double* cov) { std::memcpy(cov, P.data(), sizeof(double) * 441); }
+}  // namespace
+
+extern "C" {
+
+void orc_set_constants(double g_val, double chi_tol, int ctor_folds_chi) {
+  eigen_utils::shim_constants().g_val = g_val;
+  eigen_utils::shim_constants().chi_tol = chi_tol;
+  eigen_utils::shim_constants().ctor_folds_chi = ctor_folds_chi != 0;
+}
+
+void orc_linearization(const double* vec, const double* quat, double* Ac) {
+  RBIM A;
+  getIMUProcessLinearizationContinuous(makeState(vec, quat), A);
+  putCov(A, Ac);
+}
+
+void orc_ins_update_state(const double* gyro, const double* accel, double dt, double* vec, double* quat) {
+  RBIS s = makeState(vec, quat);
+  insUpdateState(Eigen::Vector3d(gyro[0], gyro[1], gyro[2]), Eigen::Vector3d(accel[0], accel[1], accel[2]), dt, s);
+  putState(s, vec, quat);
+}
+
+void orc_ins_update_covariance(double q_gyro, double q_accel, double q_gyro_bias, double q_accel_bias, const double* vec,
+                               const double* quat, double* cov, double dt) {
+  RBIM P = getCov(cov);
+  insUpdateCovariance(q_gyro, q_accel, q_gyro_bias, q_accel_bias, makeState(vec, quat), P, dt);
+  putCov(P, cov);
+}
+
+double orc_indexed_measurement(int m, const double* z, const double* meas_quat, const double* R, const int32_t* idx,
+                               const double* vec, const double* quat, const double* cov, double* dvec, double* dquat,
+                               double* dcov) {
+  Eigen::VectorXd zv = Eigen::Map<const Eigen::VectorXd>(z, m);
+  Eigen::MatrixXd Rm = Eigen::Map<const Eigen::MatrixXd>(R, m, m);
+  Eigen::VectorXi iv(m);
+  for (int i = 0; i < m; i++) iv(i) = idx[i];
+  RBIS ds;
+  RBIM dP;
+  double ll;
+  if (meas_quat)
+    ll = indexedPlusOrientationMeasurement(zv, Eigen::Quaterniond(meas_quat[0], meas_quat[1], meas_quat[2], meas_quat[3]), Rm, iv,
+                                           makeState(vec, quat), getCov(cov), ds, dP);
+  else
+    ll = indexedMeasurement(zv, Rm, iv, makeState(vec, quat), getCov(cov), ds, dP);
+  putState(ds, dvec, dquat);
+  putCov(dP, dcov);
+  return ll;
+}
+
+void orc_apply_delta(const double* vec, const double* quat, const double* cov, const double* dvec, const double* dquat,
+                     const double* dcov, double* pvec, double* pquat, double* pcov) {
+  RBIS post;
+  RBIM Pp;
+  rbisApplyDelta(makeState(vec, quat), getCov(cov), makeState(dvec, dquat), getCov(dcov), post, Pp);
+  putState(post, pvec, pquat);
+  putCov(Pp, pcov);
+}
+
+// ---- the reference's own update objects and history driver (rbis_update_interface.cpp:23-107,
+// update_history.cpp, mav_state_est.cpp:12-96), one MavStateEstimator per filter; same contract as the oracle's
+// orc_run_ensemble.  Too-old updates must not be passed: the reference dereferences the end() iterator that
+// addToHistory returns for them (mav_state_est.cpp:33-38).  Returns -1 (the reference does not count calls). ----
+typedef struct {
+  int32_t m, has_orient, r_mode, sensor_id;
+  int32_t idx[9];
+  int32_t _pad;
+  const double* z;
+  const double* quat;
+  const double* R;
+} orc_stream_t;
+typedef struct {
+  int32_t kind, stream;
+  int64_t row, utime;
+  double dt;
+} orc_event_t;
+
+int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, double* cov, double* loglik, int64_t utime0,
+                         const double* q_gyro, const double* q_accel, const double* q_gyro_bias, const double* q_accel_bias,
+                         const double* imu, int n_streams, const orc_stream_t* streams, int64_t n_events,
+                         const orc_event_t* events, int64_t history_span, double* trace_vec, double* trace_quat,
+                         double* trace_cov, double* trace_loglik) {
+  (void)n_streams;
+  rbis_ref_shim_history_span = history_span;
+  std::atomic<int64_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t n = next.fetch_add(1);
+      if (n >= Nf) break;
+      double v[21], q[4], P[441];
+      for (int i = 0; i < 21; i++) v[i] = vec[i * Nf + n];
+      for (int i = 0; i < 4; i++) q[i] = quat[i * Nf + n];
+      for (int i = 0; i < 441; i++) P[i] = cov[i * Nf + n];
+      RBIS s0 = makeState(v, q);
+      s0.utime = utime0;
+      MavStateEstimator est(new RBISResetUpdate(s0, getCov(P), RBISUpdateInterface::reset, utime0), (BotParam*)0);
+      const double ll0 = loglik ? loglik[n] : 0.0;
+      for (int64_t e = 0; e < n_events; e++) {
+        const orc_event_t& ev = events[e];
+        RBISUpdateInterface* u;
+        if (ev.kind == 0) {
+          Eigen::Vector3d g, a;
+          for (int i = 0; i < 3; i++) {
+            g(i) = imu[(ev.row * 6 + i) * Nf + n];
+            a(i) = imu[(ev.row * 6 + 3 + i) * Nf + n];
+          }
+          u = new RBISIMUProcessStep(g, a, q_gyro[n], q_accel[n], q_gyro_bias[n], q_accel_bias[n], ev.dt, ev.utime);
+        } else {
+          const orc_stream_t& st = streams[ev.stream];
+          const int m = st.m;
+          Eigen::VectorXd z(m);
+          Eigen::MatrixXd R = Eigen::MatrixXd::Zero(m, m);
+          Eigen::VectorXi iv(m);
+          for (int i = 0; i < m; i++) {
+            z(i) = st.z[(ev.row * m + i) * Nf + n];
+            iv(i) = st.idx[i];
+          }
+          if (st.r_mode == 0) R = Eigen::Map<const Eigen::MatrixXd>(st.R, m, m);
+          else for (int i = 0; i < m; i++) R(i, i) = st.R[i * Nf + n];
+          if (st.has_orient) {
+            const Eigen::Quaterniond mq(st.quat[(ev.row * 4 + 0) * Nf + n], st.quat[(ev.row * 4 + 1) * Nf + n],
+                                        st.quat[(ev.row * 4 + 2) * Nf + n], st.quat[(ev.row * 4 + 3) * Nf + n]);
+            u = new RBISIndexedPlusOrientationMeasurement(iv, z, R, mq, (RBISUpdateInterface::sensor_enum)st.sensor_id, ev.utime);
+          } else {
+            u = new RBISIndexedMeasurement(iv, z, R, (RBISUpdateInterface::sensor_enum)st.sensor_id, ev.utime);
+          }
+        }
+        est.addUpdate(u, true);
+        if (trace_vec || trace_quat || trace_cov || trace_loglik) {
+          RBIS hs;
+          RBIM hP;
+          est.getHeadState(hs, hP);
+          double ov[21], oq[4];
+          putState(hs, ov, oq);
+          if (trace_vec) for (int i = 0; i < 21; i++) trace_vec[(e * 21 + i) * Nf + n] = ov[i];
+          if (trace_quat) for (int i = 0; i < 4; i++) trace_quat[(e * 4 + i) * Nf + n] = oq[i];
+          if (trace_cov) for (int i = 0; i < 441; i++) trace_cov[((int64_t)e * 441 + i) * Nf + n] = hP.data()[i];
+          if (trace_loglik) trace_loglik[e * Nf + n] = ll0 + est.getMeasurementsLogLikelihood();
+        }
+      }
+      RBIS hs;
+      RBIM hP;
+      est.getHeadState(hs, hP);
+      double ov[21], oq[4];
+      putState(hs, ov, oq);
+      for (int i = 0; i < 21; i++) vec[i * Nf + n] = ov[i];
+      for (int i = 0; i < 4; i++) quat[i * Nf + n] = oq[i];
+      for (int i = 0; i < 441; i++) cov[i * Nf + n] = hP.data()[i];
+      if (loglik) loglik[n] = ll0 + est.getMeasurementsLogLikelihood();
+    }
+  };
+  if (n_threads <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  return -1;
+}
+
+}  // extern "C"

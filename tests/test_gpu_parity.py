@@ -549,3 +549,72 @@ def test_column_maps_equal_expanded_inputs_and_oracle(oracle):
                               ev, n_threads=NTHREADS)
     _assert_close(outs[0][:3], (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, "column maps")
     assert _rel_ll(outs[0][3], ref["loglik"]) < STEP_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# against fixtures produced by the REFERENCE's own code (tests/golden/rbis_reference_golden.npz, made by
+# tests/golden/make_reference_golden.py from oracle/_ref = the reference's rbis.cpp, rbis_update_interface.cpp,
+# update_history.cpp, mav_state_est.cpp compiled unmodified against stand-in dependency headers)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rbis_reference_golden.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tumbling", [("walk", False), ("tumble", True)])
+def test_fused_and_rewind_match_reference_golden(ref_golden, name, tumbling):
+    from pronto_b200.schedule import program_from_arrivals
+
+    g = ref_golden
+    sc = scenario(4, 400, tumbling=tumbling)
+    st = sc["st"]
+    with RBISBatch(4, snapshot_slots=3) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(st["events"], imu=st["imu"], streams=gpu_streams(st))
+        gv, gq, gP, gll, _ = b.get_state()
+        _assert_close((gv, gq, gP), (g[f"{name}_vec"], g[f"{name}_quat"], g[f"{name}_cov"]), STEP_TOL, name)
+        assert _rel_ll(gll, g[f"{name}_loglik"]) < STEP_TOL
+        # pose fixes 50 steps late: the reference's multimap insert + replay vs snapshot / restore / replay on the device
+        ev = st["events"]
+        pose = [e for e in ev if e[0] == 1 and e[1] == 1]
+        arrivals, pending = [], list(pose)
+        for e in ev:
+            if e[0] == 1 and e[1] == 1:
+                continue
+            arrivals.append(e)
+            while pending and e[0] == 0 and e[3] >= pending[0][3] + 50_000:
+                arrivals.append(pending.pop(0))
+        arrivals += pending
+        ops, cnt = program_from_arrivals(arrivals, snapshot_slots=3, snapshot_period_us=100_000, snapshot_phase_us=1000)
+        assert cnt["rewinds"] == len(pose)
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(ops, imu=st["imu"], streams=gpu_streams(st))
+        gv, gq, gP, gll, _ = b.get_state()
+        _assert_close((gv, gq, gP), (g[f"{name}_late_vec"], g[f"{name}_late_quat"], g[f"{name}_late_cov"]), STEP_TOL, name + " late")
+        assert _rel_ll(gll, g[f"{name}_late_loglik"]) < STEP_TOL
+
+
+@pytest.mark.gpu
+def test_single_updates_match_reference_golden(ref_golden):
+    g = ref_golden
+    N = 5
+    rep = lambda a: np.repeat(np.asarray(a)[:, None], N, axis=1)
+    vec, quat, cov = rep(g["op_vec"]), rep(g["op_quat"]), rep(g["op_cov"].T.reshape(-1))
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(vec, quat, cov)
+        b.ins_step(rep(g["op_gyro"]), rep(g["op_accel"]), 1e-3)
+        gv, gq, gP, _, _ = b.get_state()
+        assert np.max(np.abs(gv - g["op_ins_vec"][:, None])) < 1e-13 and np.max(np.abs(gq - g["op_ins_quat"][:, None])) < 1e-13
+        assert np.max(np.abs(gP - g["op_ins_cov"].T.reshape(-1)[:, None])) < 1e-14
+        for c in range(int(g["n_meas_cases"])):
+            b.set_state(vec, quat, cov)
+            mq = g[f"m{c}_mq"]
+            b.indexed_update([int(i) for i in g[f"m{c}_idx"]], rep(g[f"m{c}_z"]), g[f"m{c}_R"], quat=rep(mq) if mq.size else None)
+            gv, gq, gP, gll, _ = b.get_state()
+            assert np.max(np.abs(gv - g[f"m{c}_vec"][:, None])) < 1e-11, c
+            assert np.max(np.abs(gq - g[f"m{c}_quat"][:, None])) < 1e-11, c
+            assert np.max(np.abs(gP - g[f"m{c}_cov"].T.reshape(-1)[:, None])) < 1e-12, c
+            assert np.max(np.abs(gll - float(g[f"m{c}_ll"]))) < 1e-9 * max(1.0, abs(float(g[f"m{c}_ll"]))), c
