@@ -2,7 +2,7 @@
 # Builds dev/kbench (developer micro-benchmark): one object per kernel variant.
 set -e
 cd "$(dirname "$0")"
-NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr"
+NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -fmad=false"
 mkdir -p _build
 objs=""
 i=0

@@ -61,6 +61,8 @@ int main(int argc, char** argv) {
   long long N = argc > 1 ? atoll(argv[1]) : 65536;
   int T = argc > 2 ? atoi(argv[2]) : 200;
   const char* only = argc > 3 ? argv[3] : nullptr;
+  if (only && !strcmp(only, "-")) only = nullptr;
+  const bool decoupled = argc > 4 ? atoi(argv[4]) != 0 : true;  // zero omega / a couplings in the initial covariance
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s, %d SMs, N=%lld T=%d\n", prop.name, prop.multiProcessorCount, N, T);
@@ -111,7 +113,13 @@ int main(int argc, char** argv) {
     double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     for (int i = 0; i < 4; i++) quat[i * N + n] = q[i] / nn;
     for (int j = 0; j < 21; j++)
-      for (int i = 0; i <= j; i++) P[(size_t)(j * (j + 1) / 2 + i) * N + n] = (i == j) ? 0.01 * (1 + 0.1 * rnd()) : 1e-4 * rnd();
+      for (int i = 0; i <= j; i++) {
+        auto passive = [](int k) { return k < 3 || (k >= 12 && k < 15); };
+        const bool blk = (j < 3) || (i >= 12 && j < 15);
+        double v = (i == j) ? 0.01 * (1 + 0.1 * rnd()) : 1e-4 * rnd();
+        if (decoupled && (passive(i) || passive(j)) && !blk) v = 0.0;
+        P[(size_t)(j * (j + 1) / 2 + i) * N + n] = v;
+      }
     q4[n] = 7.6e-5; q4[N + n] = 1e-2; q4[2 * N + n] = 3e-10; q4[3 * N + n] = 1e-6;
     for (int i = 0; i < pi; i++) for (int c = 0; c < 4; c++) q1[((size_t)i * 4 + c) * N + n] = quat[c * N + n];
   }

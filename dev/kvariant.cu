@@ -7,7 +7,11 @@
 #define KFUNC rbis_fused_kernel
 #define SET_FAST(s, c, v)
 #else
+#ifdef KDC
+#define KFUNC rbis_fused_kernel<false, true>
+#else
 #define KFUNC rbis_fused_kernel<false>
+#endif
 #define SET_FAST(s, c, v) s.chunk_fast[c] = v
 #endif
 #ifndef KHEADER

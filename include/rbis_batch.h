@@ -80,7 +80,13 @@ typedef struct {
                               consecutive rbis_batch_run_fused calls overlap and the last, partially filled wave of
                               one launch does not idle SMs; 0 = automatic (4 when the CTAs do not fill whole
                               waves, else 1), 1 = off, max 8 */
-  int32_t reserved;
+  int32_t dense_only;      /* 0 (default) = automatic: fused programs run the "decoupled" kernel variant (only the
+                              15x15 block of v, chi, p, b_g, b_a on chip, 384 filters per SM) whenever every filter's
+                              covariance couplings to the omega / a rows are exactly zero -- true for every filter
+                              started from the reference's diagonal initial covariance (MSE/rbis_initializer.cpp:85-91)
+                              until a measurement indexes omega or a -- and the program has only aligned-triple
+                              measurement chunks on other indices; results are bit-identical to the dense variant.
+                              1 = always run the dense variant (whole covariance on chip, 256 filters per SM). */
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /
@@ -122,6 +128,9 @@ int64_t rbis_batch_num_filters(const rbis_batch_t* h);
 void* rbis_batch_stream(rbis_batch_t* h);
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t rbis_batch_launch_count(const rbis_batch_t* h);
+/* Kernel variant the last rbis_batch_run_fused / single-op call launched: 0 dense, 1 dense with the general
+ * measurement path, 2 decoupled (see rbis_batch_config_t::dense_only); -1 before the first launch. */
+int rbis_batch_last_kernel_variant(const rbis_batch_t* h);
 
 /* ---- RBISResetUpdate::updateFilter (MSE/rbis_update_interface.cpp:23-28): posterior := given,
  * loglikelihood := 0 (or `loglik` [N] when non-NULL).  cov may be NULL to keep the current one. */

@@ -70,7 +70,7 @@ class RBISBatch:
     """An ensemble of N RBIS filters on one GPU (rbis_batch_t)."""
 
     def __init__(self, n_filters, device=0, g_val=9.8, chi_tol=1e-6, ctor_folds_chi=True, renormalize_quat=False,
-                 snapshot_slots=0, launch_groups=0):
+                 snapshot_slots=0, launch_groups=0, dense_only=False):
         self.lib = capi.load()
         cfg = capi.Config()
         self.lib.rbis_default_config(C.byref(cfg))
@@ -78,6 +78,7 @@ class RBISBatch:
         cfg.ctor_folds_chi, cfg.renormalize_quat = int(bool(ctor_folds_chi)), int(bool(renormalize_quat))
         cfg.snapshot_slots, cfg.device = int(snapshot_slots), int(device)
         cfg.launch_groups = int(launch_groups)
+        cfg.dense_only = int(bool(dense_only))
         self.h = C.c_void_p()
         capi.check(self.lib.rbis_batch_create(C.byref(self.h), int(n_filters), C.byref(cfg)))
         self.N = int(n_filters)
@@ -254,6 +255,11 @@ class RBISBatch:
     @property
     def launch_count(self):
         return int(self.lib.rbis_batch_launch_count(self.h))
+
+    @property
+    def last_kernel_variant(self):
+        """0 dense, 1 dense + general measurement path, 2 decoupled (rbis_batch_config_t::dense_only); -1 before any."""
+        return int(self.lib.rbis_batch_last_kernel_variant(self.h))
 
     @property
     def cuda_stream(self):

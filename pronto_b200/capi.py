@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("snapshot_slots", C.c_int32),
         ("device", C.c_int32),
         ("launch_groups", C.c_int32),
-        ("reserved", C.c_int32),
+        ("dense_only", C.c_int32),
     ]
 
 
@@ -72,6 +72,7 @@ PROTOTYPES = {
     "rbis_batch_num_filters": (C.c_int64, [C.c_void_p]),
     "rbis_batch_stream": (C.c_void_p, [C.c_void_p]),
     "rbis_batch_launch_count": (C.c_int64, [C.c_void_p]),
+    "rbis_batch_last_kernel_variant": (C.c_int, [C.c_void_p]),
     "rbis_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "rbis_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),
     "rbis_batch_set_filter": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),

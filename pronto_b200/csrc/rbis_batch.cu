@@ -12,8 +12,21 @@
 #include <vector>
 
 #include "../../include/rbis_batch.h"
+#include "rbis_kernels.cuh"   // namespace rbisk: 256 filters per CTA, whole covariance on chip (any filter, any program)
+// Second configuration of the same device code, namespace rbisk_dc: 384 filters per CTA, only the 15x15 active block
+// on chip -- the DC ("decoupled") kernels for ensembles whose omega / a couplings are exactly zero (rbis_kernels.cuh).
+#define rbisk rbisk_dc
+#define RBIS_FUSED_ONLY 1
+#undef RBIS_TPB
+#define RBIS_TPB 384
+#undef RBIS_PLACEMENT
+#define RBIS_PLACEMENT 2
+#undef RBIS_LATE_LOADS
+#define RBIS_LATE_LOADS 1
 #include "rbis_kernels.cuh"
+#undef rbisk
 #include "rbis_stats.cuh"
+static_assert(sizeof(rbisk::KParams) == sizeof(rbisk_dc::KParams), "both kernel configurations take the same parameter block");
 
 namespace {
 
@@ -89,6 +102,13 @@ struct rbis_batch {
   double* qparams = nullptr;  // [4][N]
   double* snap = nullptr;
   std::vector<char> snap_valid;
+  // ---- decoupled-filter tracking (rbis_kernels.cuh, "decoupled filters"): are the omega / a couplings of every
+  // filter's covariance exactly zero?  -1 unknown (checked on the device before the next eligible fused launch),
+  // 0 no, 1 yes.  snap_dc[slot] is the same for the content of a snapshot slot (0 = no or unknown).
+  int decoupled = -1;
+  std::vector<char> snap_dc;
+  int* d_flag = nullptr;
+  int last_variant = -1;  // kernel variant of the last fused launch: 0 dense, 1 dense + general measurements, 2 decoupled
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
   DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
@@ -126,6 +146,19 @@ struct rbis_batch {
 namespace {
 
 constexpr int kSmemBytes = rbisk::SMEM_BYTES;
+constexpr int kSmemBytesDc = rbisk_dc::SMEM_BYTES;
+
+void launch_variant(int variant, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
+  if (variant == 2) {
+    rbisk_dc::KParams kd;
+    std::memcpy(&kd, &kp, sizeof(kd));
+    rbisk_dc::rbis_fused_kernel<false, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
+  } else if (variant == 1) {
+    rbisk::rbis_fused_kernel<true><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+  } else {
+    rbisk::rbis_fused_kernel<false><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+  }
+}
 
 int use_device(const rbis_batch* h) {
   cudaError_t e = cudaSetDevice(h->cfg.device);
@@ -214,6 +247,10 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   // ---- validate ops and translate ----
   std::vector<rbisk::Op> kops((size_t)n_ops);
   std::vector<char> snap_valid = h->snap_valid;
+  // decoupled-kernel eligibility of the program: every RESTORE must read a slot whose content is decoupled (written
+  // by a decoupled launch, or by an earlier SNAPSHOT of this program)
+  std::vector<char> snap_dc = h->snap_dc;
+  bool restores_ok = true, any_snapshot = false;
   int64_t last_utime = h->utime;
   for (int64_t i = 0; i < n_ops; i++) {
     const rbis_op_t& o = ops[i];
@@ -234,10 +271,13 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       case RBIS_OP_SNAPSHOT:
         if (o.row < 0 || o.row >= h->cfg.snapshot_slots) return fail(RBIS_ERR_INVALID, "op %lld: snapshot slot %lld out of range (%d slots)", (long long)i, (long long)o.row, h->cfg.snapshot_slots);
         snap_valid[(size_t)o.row] = 1;
+        snap_dc[(size_t)o.row] = 2;  // "as this launch": resolved once the variant is known
+        any_snapshot = true;
         break;
       case RBIS_OP_RESTORE:
         if (o.row < 0 || o.row >= h->cfg.snapshot_slots) return fail(RBIS_ERR_INVALID, "op %lld: snapshot slot %lld out of range (%d slots)", (long long)i, (long long)o.row, h->cfg.snapshot_slots);
         if (!snap_valid[(size_t)o.row]) return fail(RBIS_ERR_STATE, "op %lld: restore of empty snapshot slot %lld", (long long)i, (long long)o.row);
+        if (!snap_dc[(size_t)o.row]) restores_ok = false;
         last_utime = o.utime;
         break;
       default:
@@ -282,6 +322,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * 81, 0.0);
   bool any_shared = false;
   bool needs_general = false;  // some chunk is not an aligned triple -> kernel variant with the general path
+  bool passive_index = false;  // some stream measures omega or a directly -> couplings become non-zero
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
     rbisk::StreamDesc& d = kp.streams[s];
@@ -299,6 +340,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (in.rows == 0) { d.n_chunks = 0; continue; }
     plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
     mark_fast_chunks(d, &needs_general);
+    for (int a = 0; a < in.m; a++)
+      if (!rbisk::is_act(in.idx[a])) passive_index = true;
     if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, &d.z)) return rc;
     if (in.has_orientation)
       if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
@@ -311,7 +354,24 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     }
   }
   if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
-  const unsigned grid = (unsigned)((N + rbisk::TPB - 1) / rbisk::TPB);
+  // ---- kernel variant ----
+  int variant = needs_general ? 1 : 0;
+  const bool dc_eligible = !h->cfg.dense_only && !needs_general && !passive_index && restores_ok;
+  if (dc_eligible && h->decoupled < 0) {
+    // one device pass over the couplings, then a host read: happens once after set_state / set_filter, not per launch
+    if (int rc = main_stream_work(h)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    rbisk::coupling_check_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->P, (long long)N, h->d_flag);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->decoupled = flag ? 0 : 1;
+  }
+  if (dc_eligible && h->decoupled == 1) variant = 2;
+  const int tpb = variant == 2 ? rbisk_dc::TPB : rbisk::TPB;
+  const unsigned grid = (unsigned)((N + tpb - 1) / tpb);
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
     if (staging) CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
@@ -333,8 +393,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     kp.ops = h->d_ops;
     kp.block_offset = 0;
-    if (needs_general) rbisk::rbis_fused_kernel<true><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
-    else rbisk::rbis_fused_kernel<false><<<grid, rbisk::TPB, kSmemBytes, h->stream>>>(kp);
+    launch_variant(variant, grid, h->stream, kp);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
@@ -365,8 +424,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
       if (b1 > b0) {
         kp.block_offset = (int)b0;
-        if (needs_general) rbisk::rbis_fused_kernel<true><<<b1 - b0, rbisk::TPB, kSmemBytes, gs>>>(kp);
-        else rbisk::rbis_fused_kernel<false><<<b1 - b0, rbisk::TPB, kSmemBytes, gs>>>(kp);
+        launch_variant(variant, b1 - b0, gs, kp);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
       }
@@ -380,6 +438,20 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   }
   h->launch_seq++;
   h->snap_valid = snap_valid;
+  // ---- what the launch leaves behind ----
+  // A dense launch keeps exact zeros exact unless it measured omega / a or restored a slot of unknown content.
+  const int before = h->decoupled;
+  if (variant != 2) {
+    if (passive_index) h->decoupled = 0;
+    else if (!restores_ok) h->decoupled = -1;
+  }
+  if (any_snapshot) {
+    const char as_launch = (variant == 2 || (before == 1 && !passive_index && restores_ok)) ? 1 : 0;
+    for (auto& f : snap_dc)
+      if (f == 2) f = as_launch;
+  }
+  h->snap_dc = snap_dc;
+  h->last_variant = variant;
   h->utime = last_utime;
   return 0;
 }
@@ -399,7 +471,7 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->snapshot_slots = 0;
   cfg->device = 0;
   cfg->launch_groups = 0;
-  cfg->reserved = 0;
+  cfg->dense_only = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -447,8 +519,10 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   {
     // launch groups: explicit, or automatic = 4 when the CTAs do not fill a whole number of waves
     const long long ctas = (long long)((n_filters + rbisk::TPB - 1) / rbisk::TPB), sms = prop.multiProcessorCount;
+    const long long ctas_dc = (long long)((n_filters + rbisk_dc::TPB - 1) / rbisk_dc::TPB);
     int g = c.launch_groups;
-    if (g == 0) g = (ctas > sms && ctas % sms != 0) ? 4 : 1;
+    if (g == 0) g = ((ctas > sms && ctas % sms != 0) || (!c.dense_only && ctas_dc > sms && ctas_dc % sms != 0)) ? 4 : 1;
+    if ((long long)g > ctas_dc) g = (int)ctas_dc;
     if ((long long)g > ctas) g = (int)ctas;
     h->n_groups = g < 1 ? 1 : g;
   }
@@ -476,7 +550,10 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   if (c.snapshot_slots > 0) {
     CREATE_TRY(cudaMalloc(&h->snap, (size_t)c.snapshot_slots * rbisk::SNAP_ROWS * N * sizeof(double)));
     h->snap_valid.assign((size_t)c.snapshot_slots, 0);
+    h->snap_dc.assign((size_t)c.snapshot_slots, 0);
   }
+  CREATE_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   // default state: zeros, identity quaternion, zero covariance, zero process noise
@@ -510,7 +587,7 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   }
   if (h->pre_evt) cudaEventDestroy(h->pre_evt);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
-  cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared);
+  cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag);
   for (auto& m : h->d_map) cudaFree(m);
   h->full_cov.release(); h->misc.release(); h->stats_async.release();
   for (auto& s : h->slots) {
@@ -541,6 +618,7 @@ int rbis_batch_synchronize(rbis_batch_t* h) {
 int64_t rbis_batch_num_filters(const rbis_batch_t* h) { return h ? h->N : 0; }
 void* rbis_batch_stream(rbis_batch_t* h) { return h ? (void*)h->stream : nullptr; }
 int64_t rbis_batch_launch_count(const rbis_batch_t* h) { return h ? h->launches : 0; }
+int rbis_batch_last_kernel_variant(const rbis_batch_t* h) { return h ? h->last_variant : -1; }
 
 int rbis_batch_set_state(rbis_batch_t* h, const double* vec, const double* quat, const double* cov,
                          const double* loglik, int64_t utime, int mem) {
@@ -563,6 +641,7 @@ int rbis_batch_set_state(rbis_batch_t* h, const double* vec, const double* quat,
     rbisk::pack_cov_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(src, h->P, (long long)N);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    h->decoupled = -1;
   }
   if (loglik) CUDA_TRY(cudaMemcpyAsync(h->loglik, loglik, N * sizeof(double), kind, h->stream));
   else CUDA_TRY(cudaMemsetAsync(h->loglik, 0, N * sizeof(double), h->stream));
@@ -612,6 +691,14 @@ int rbis_batch_set_filter(rbis_batch_t* h, int64_t n, const double* vec, const d
     for (int j = 0; j < 21; j++)
       for (int i = 0; i <= j; i++) packed[rbisk::slot(i, j)] = cov[i + 21 * j];
     CUDA_TRY(cudaMemcpy2DAsync(h->P + n, pitch, packed, sizeof(double), sizeof(double), rbisk::NP, cudaMemcpyHostToDevice, h->stream));
+    if (h->decoupled == 1) {
+      // stays decoupled when the new covariance is: checked on the host, no device pass needed
+      for (int j = 0; j < 21 && h->decoupled == 1; j++)
+        for (int i = 0; i <= j; i++) {
+          const bool blk = (j < 3) || (i >= 12 && j < 15);
+          if (!(rbisk::is_act(i) && rbisk::is_act(j)) && !blk && !(packed[rbisk::slot(i, j)] == 0.0)) { h->decoupled = 0; break; }
+        }
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(h->loglik + n, &loglik, sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -20,7 +20,12 @@
 //   meas3<I0>() / meas_general() = matrixMeasurementGetKandCovDelta + indexed[PlusOrientation]Measurement
 //                      + the covariance half of rbisApplyDelta                      rbis.cpp:124-227
 //   meas_finish()    = the state half of rbisApplyDelta (addState)                  rbis.cpp:219-227
-#pragma once
+// Include guard for the default configuration only: rbis_batch.cu (and dev/kvariant.cu) include this file again with
+// `#define rbisk <other namespace>` and different RBIS_TPB / RBIS_PLACEMENT knobs, once per kernel configuration.
+#if defined(rbisk) || !defined(RBIS_KERNELS_CUH_DEFAULT)
+#ifndef rbisk
+#define RBIS_KERNELS_CUH_DEFAULT
+#endif
 #include <cstdint>
 #include <utility>
 
@@ -95,9 +100,21 @@ __host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s)
 //   placement 1: the reverse -- the active part (5.5 accesses per slot and step, most values used by several
 //                FMAs) in shared memory, whose loads land in any register, and the passive part (2-3 accesses)
 //                in tensor memory; 113 slots fit in shared memory, so the (b_a,b_a) block and (17,17) stay in TMEM.
+//   placement 2 (DC kernels only, 384 filters per CTA): only the 120 active slots are on chip; the 9x9 block of
+//                p, b_g, b_a (45 slots, the least accessed: 1-3 loads and at most one store per step) in tensor
+//                memory, the 75 slots that involve v or chi in shared memory.
+__host__ __device__ constexpr bool on_chip(int i, int j) {
+#if RBIS_PLACEMENT == 2
+  return is_act(i) && is_act(j);
+#else
+  return true;
+#endif
+}
 __host__ __device__ constexpr bool slot_in_tm(int i, int j) {
 #if RBIS_PLACEMENT == 0
   return is_act(i) && is_act(j);
+#elif RBIS_PLACEMENT == 2
+  return (i >= 9 && !(i >= 12 && i < 15)) && (j >= 9 && !(j >= 12 && j < 15));
 #else
   return !(is_act(i) && is_act(j)) || i >= 18 || (i == 17 && j == 17);
 #endif
@@ -114,6 +131,7 @@ constexpr Placement make_placement() {
     for (int i = 0; i <= j; i++) {
       const int s_ = slot(i, j);
       pl.tm[s_] = slot_in_tm(i, j);
+      if (!on_chip(i, j)) { pl.idx[s_] = -1; continue; }
       pl.idx[s_] = (short)(pl.tm[s_] ? nt++ : ns++);
     }
   pl.n_tm = nt;
@@ -129,9 +147,46 @@ __host__ __device__ constexpr int sm_index(int i, int j) { return kPlace.idx[slo
 
 constexpr int N_TM = kPlace.n_tm;   // slots in tensor memory
 constexpr int N_SM = kPlace.n_sm;   // slots in shared memory
-static_assert(N_TM + 10 * RBIS_PARK_STATE_SLOTS <= 128, "a thread owns 128 doubles of tensor memory");
+// tensor memory: 128 lanes x 512 columns; warp w reaches lanes 32*(w%4)..+31 only, so the TPB/128 warps that share a
+// lane quarter split the 512 columns: TM_COLS 32-bit columns = TM_COLS/2 doubles per thread
+constexpr int TM_COLS = (512 / ((TPB + 127) / 128)) & ~1;
+static_assert(TPB % 32 == 0, "whole warps");
+static_assert(2 * (N_TM + 10 * RBIS_PARK_STATE_SLOTS) <= TM_COLS, "tensor-memory share of a thread exceeded");
 static_assert(N_SM * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
 constexpr int SMEM_BYTES = N_SM * TPB * 8;
+
+// ---- decoupled filters (DC kernels) ---------------------------------------------------------------
+// The rows of Ad for omega (0..2) and a (12..14) are identity and its columns for them are zero, so the couplings
+// P[{omega,a}, .] never feed the 15x15 active block (v, chi, p, b_g, b_a); they only evolve by left-multiplication
+// (Ad, I - K H).  A filter whose couplings are exactly zero -- every filter initialised with the reference's diagonal
+// covariance, MSE/rbis_initializer.cpp:85-91 -- keeps them exactly zero until a measurement indexes omega or a, and
+// the (omega,omega) / (a,a) blocks are overwritten by every IMU step (rbis.cpp:120-121).  The DC kernel variants
+// exploit that, verified at run time by the host (coupling_check_kernel): they keep only the 120 active slots on
+// chip and touch nothing else; results are bit-identical to the dense variants.
+constexpr int N_ACT = 15;
+constexpr int NP_ACT = N_ACT * (N_ACT + 1) / 2;
+__host__ __device__ constexpr int act_col(int k) { return k < 9 ? 3 + k : 6 + k; }   // k-th active index
+__host__ __device__ constexpr int act_pos(int c) { return c < 12 ? c - 3 : c - 6; }  // inverse
+struct ActSlots {
+  short s[NP_ACT];   // packed slots with both indices active, ascending
+  short rest[NP - NP_ACT - 12];  // passive couplings (everything else except the (omega,omega) and (a,a) blocks)
+  short blk[12];     // (omega,omega) then (a,a) blocks, upper triangles column by column
+};
+constexpr ActSlots make_act_slots() {
+  ActSlots a{};
+  int na = 0, nr = 0, nb = 0;
+  for (int j = 0; j < NS; j++)
+    for (int i = 0; i <= j; i++) {
+      const bool blk = (j < 3) || (i >= 12 && j < 15);
+      if (is_act(i) && is_act(j)) a.s[na++] = (short)slot(i, j);
+      else if (blk) a.blk[nb++] = (short)slot(i, j);
+      else a.rest[nr++] = (short)slot(i, j);
+    }
+  return a;
+}
+constexpr ActSlots kAct = make_act_slots();
+__constant__ ActSlots c_act = make_act_slots();  // run-time indexable copy
+constexpr int N_REST = NP - NP_ACT - 12;
 
 struct StreamDesc {
   int m, has_orient, r_mode, n_chunks;
@@ -187,9 +242,13 @@ __device__ __forceinline__ void static_for(F&& f) {
 struct V3 {
   double x, y, z;
 };
+// The library is compiled with -fmad=false: every fused multiply-add is written out, so that all kernel variants and
+// configurations of this file perform the same arithmetic bit for bit (the compiler's own contraction choices
+// differ between instantiations).
 __device__ __forceinline__ V3 cross(const V3& a, const V3& b) {
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+  return {fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))};
 }
+__device__ __forceinline__ double sumsq3(double x, double y, double z) { return fma(z, z, fma(y, y, x * x)); }
 // acc + a x b  /  acc - a x b  as two FMAs per component
 __device__ __forceinline__ V3 add_cross(const V3& acc, const V3& a, const V3& b) {
   return {fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)), fma(a.x, b.y, fma(-a.y, b.x, acc.z))};
@@ -210,11 +269,11 @@ struct Q4 {
   double w, x, y, z;
 };
 __device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
-  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
-          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+  return {fma(-a.z, b.z, fma(-a.y, b.y, fma(-a.x, b.x, a.w * b.w))), fma(-a.z, b.y, fma(a.y, b.z, fma(a.x, b.w, a.w * b.x))),
+          fma(-a.x, b.z, fma(a.z, b.x, fma(a.y, b.w, a.w * b.y))), fma(-a.y, b.x, fma(a.x, b.y, fma(a.z, b.w, a.w * b.z)))};
 }
 __device__ __forceinline__ Q4 qinv(const Q4& q) {
-  const double n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+  const double n2 = fma(q.z, q.z, fma(q.y, q.y, fma(q.x, q.x, q.w * q.w)));
   if (n2 > 0) {
     const double r = 1.0 / n2;  // Eigen divides each coefficient; 1 ulp apart at most
     return {q.w * r, -q.x * r, -q.y * r, -q.z * r};
@@ -226,7 +285,7 @@ __device__ __forceinline__ V3 qrot(const Q4& q, const V3& v) {
   V3 uv = cross(u, v);
   uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
   V3 c = cross(u, uv);
-  return {v.x + q.w * uv.x + c.x, v.y + q.w * uv.y + c.y, v.z + q.w * uv.z + c.z};
+  return {fma(q.w, uv.x, v.x) + c.x, fma(q.w, uv.y, v.y) + c.y, fma(q.w, uv.z, v.z) + c.z};
 }
 // quaternion of AngleAxis(|chi|, chi/|chi|)
 __device__ __forceinline__ Q4 qexp(const V3& chi, double n) {
@@ -237,7 +296,7 @@ __device__ __forceinline__ Q4 qexp(const V3& chi, double n) {
 // subtractQuats(q1, q2) = axis*angle of q2^-1 * q1 (Eigen >= 3.3 AngleAxis, bot_mod2pi)
 __device__ __forceinline__ V3 subtract_quats(const Q4& q1, const Q4& q2) {
   const Q4 r = qmul(qinv(q2), q1);
-  double n = sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+  double n = sqrt(sumsq3(r.x, r.y, r.z));
   if (n == 0.0) return {0, 0, 0};
   double angle = 2.0 * atan2(n, fabs(r.w));
   if (r.w < 0) n = -n;
@@ -394,6 +453,23 @@ struct SlotRun {
   static constexpr int col(int k) { return col_of_slot(S0 + k); }
 };
 
+// active packed slots kAct.s[K0 .. K0+N-1]
+template <int K0, int N_>
+struct ActRun {
+  static constexpr int N = N_;
+  static constexpr int row(int k) { return row_of_slot(kAct.s[K0 + k]); }
+  static constexpr int col(int k) { return col_of_slot(kAct.s[K0 + k]); }
+};
+// the slots a whole-covariance sweep visits: all 231 (dense) or the 120 active ones (DC)
+template <bool DC, int K0, int N_>
+struct SweepRun_ { using type = SlotRun<K0, N_>; };
+template <int K0, int N_>
+struct SweepRun_<true, K0, N_> { using type = ActRun<K0, N_>; };
+template <bool DC, int K0, int N_>
+using SweepRun = typename SweepRun_<DC, K0, N_>::type;
+template <bool DC>
+constexpr int kSweepLen = DC ? NP_ACT : NP;
+
 template <int... Cs>
 struct ColList {
   static constexpr int n = (int)sizeof...(Cs);
@@ -493,18 +569,20 @@ template <int C> using FetchAll = ColRows<C, 3, 6, 9, 15, 18>;
 struct QNoise {
   double q_gyro, q_accel, q_gyro_bias, q_accel_bias;
 };
-template <class AfterPassive, class BeforeEv>
+template <bool DC, class AfterPassive, class BeforeEv>
 __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive&& after_passive, BeforeEv&& before_ev) {
   const double dt = L.dt;
   // ---------------- passive columns omega (0..2), a (12..14): all three congruences in one pass ----------------
-  for_columns<FetchAll>(P, ColList<0, 1, 2, 12, 13, 14>{}, [&](auto cc, const double* d, auto) {
-    constexpr int c = cc;
-    const V3 pv = v3at(d, 0), pc = v3at(d, 1), pp = v3at(d, 2), pg = v3at(d, 3), pa = v3at(d, 4);
-    P.setcol3<9, c>(zp(L, pv, pc, pp));
-    P.setcol3<3, c>(zv(L, pv, pc, pg, pa));
-    P.setcol3<6, c>(zc(L, pc, pg));
-    RBIS_SCHED_FENCE();
-  });
+  if constexpr (!DC) {
+    for_columns<FetchAll>(P, ColList<0, 1, 2, 12, 13, 14>{}, [&](auto cc, const double* d, auto) {
+      constexpr int c = cc;
+      const V3 pv = v3at(d, 0), pc = v3at(d, 1), pp = v3at(d, 2), pg = v3at(d, 3), pa = v3at(d, 4);
+      P.setcol3<9, c>(zp(L, pv, pc, pp));
+      P.setcol3<3, c>(zv(L, pv, pc, pg, pa));
+      P.setcol3<6, c>(zc(L, pc, pg));
+      RBIS_SCHED_FENCE();
+    });
+  }
   const QNoise qn = after_passive();
   const double q_gyro = qn.q_gyro, q_accel = qn.q_accel, q_gyro_bias = qn.q_gyro_bias, q_accel_bias = qn.q_accel_bias;
   // ---------------- E_p on the active block: block row p (9..11), sources v (3..5), chi (6..8) ----------------
@@ -553,7 +631,7 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive
       } else {
         constexpr int k = c % 3;
         Zb[k] = z;
-        if constexpr (c >= 18) P.set<c, c>(d[9 + k] + q_accel_bias * dt);  // Qd[ba,ba]; (ba,ba) is not read again in this step
+        if constexpr (c >= 18) P.set<c, c>(fma(q_accel_bias, dt, d[9 + k]));  // Qd[ba,ba]; (ba,ba) is not read again in this step
         if constexpr (k == 2) {
           if constexpr (c == 5) {
             Nv[0] = Zb[0]; Nv[1] = Zb[1]; Nv[2] = Zb[2];
@@ -568,13 +646,13 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive
             static_for<3>([&](auto kk) { Nv[kk] = axpy(-dt, Zb[kk], Nv[kk]); });
             static_for<3>([&](auto kk) { P.setcol3<3, 18 + kk>(Zb[kk]); });
             // Qd[v,v] = dt (q_gyro (|v|^2 I - v v^T) + q_accel I)      (rbis.cpp:91-116)
-            const double vv = L.v.x * L.v.x + L.v.y * L.v.y + L.v.z * L.v.z;
-            P.set<3, 3>(Nv[0].x + (qg * (vv - L.v.x * L.v.x) + qa));
-            P.set<3, 4>(Nv[1].x + (qg * (-L.v.x * L.v.y)));
-            P.set<3, 5>(Nv[2].x + (qg * (-L.v.x * L.v.z)));
-            P.set<4, 4>(Nv[1].y + (qg * (vv - L.v.y * L.v.y) + qa));
-            P.set<4, 5>(Nv[2].y + (qg * (-L.v.y * L.v.z)));
-            P.set<5, 5>(Nv[2].z + (qg * (vv - L.v.z * L.v.z) + qa));
+            const double vv = sumsq3(L.v.x, L.v.y, L.v.z);
+            P.set<3, 3>(Nv[0].x + fma(qg, fma(-L.v.x, L.v.x, vv), qa));
+            P.set<3, 4>(fma(qg, -L.v.x * L.v.y, Nv[1].x));
+            P.set<3, 5>(fma(qg, -L.v.x * L.v.z, Nv[2].x));
+            P.set<4, 4>(Nv[1].y + fma(qg, fma(-L.v.y, L.v.y, vv), qa));
+            P.set<4, 5>(fma(qg, -L.v.y * L.v.z, Nv[2].y));
+            P.set<5, 5>(Nv[2].z + fma(qg, fma(-L.v.z, L.v.z, vv), qa));
           }
         }
       }
@@ -598,7 +676,7 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive
         constexpr int k = c - 15;
         Mc[k] = axpy(-dt, z, Mc[k]);
         P.setcol3<6, c>(z);
-        P.set<c, c>(d[3 + k] + q_gyro_bias * dt);  // Qd[bg,bg]; (bg,bg) is not read again in this step
+        P.set<c, c>(fma(q_gyro_bias, dt, d[3 + k]));  // Qd[bg,bg]; (bg,bg) is not read again in this step
         if constexpr (c == 17) {
           P.set<6, 6>(Mc[0].x + qg); P.set<6, 7>(Mc[1].x); P.set<6, 8>(Mc[2].x);
           P.set<7, 7>(Mc[1].y + qg); P.set<7, 8>(Mc[2].y);
@@ -615,18 +693,21 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive
     });
   }
   tm_wait_st();
-  // overwrites of rbis.cpp:120-121 (nothing in this step reads these blocks)
-  P.set<12, 12>(q_accel); P.set<13, 13>(q_accel); P.set<14, 14>(q_accel);
-  P.set<12, 13>(0.0); P.set<12, 14>(0.0); P.set<13, 14>(0.0);
-  P.set<0, 0>(q_gyro); P.set<1, 1>(q_gyro); P.set<2, 2>(q_gyro);
-  P.set<0, 1>(0.0); P.set<0, 2>(0.0); P.set<1, 2>(0.0);
-  tm_wait_st();
+  // overwrites of rbis.cpp:120-121 (nothing in this step reads these blocks; the DC kernel writes them to global
+  // memory when a snapshot or the end of the program needs them)
+  if constexpr (!DC) {
+    P.set<12, 12>(q_accel); P.set<13, 13>(q_accel); P.set<14, 14>(q_accel);
+    P.set<12, 13>(0.0); P.set<12, 14>(0.0); P.set<13, 14>(0.0);
+    P.set<0, 0>(q_gyro); P.set<1, 1>(q_gyro); P.set<2, 2>(q_gyro);
+    P.set<0, 1>(0.0); P.set<0, 2>(0.0); P.set<1, 2>(0.0);
+    tm_wait_st();
+  }
 }
 
 // chiToQuat on the filter state: fold vec chi into the quaternion when its norm exceeds the tolerance
 __device__ __forceinline__ void fold_chi(FilterState& s, double chi_tol) {
   const V3 c{s.x[6], s.x[7], s.x[8]};
-  const double n = sqrt(c.x * c.x + c.y * c.y + c.z * c.z);
+  const double n = sqrt(sumsq3(c.x, c.y, c.z));
   if (n > chi_tol) {
     const Q4 q = qmul({s.qw, s.qx, s.qy, s.qz}, qexp(c, n));
     s.qw = q.w; s.qx = q.x; s.qy = q.y; s.qz = q.z;
@@ -645,7 +726,7 @@ __device__ __forceinline__ void add_state_tail(FilterState& s, const V3& dchi, b
     s.qw = q.w; s.qx = q.x; s.qy = q.y; s.qz = q.z;
   }
   if (renorm) {
-    const double r = 1.0 / sqrt(s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz);
+    const double r = 1.0 / sqrt(fma(s.qz, s.qz, fma(s.qy, s.qy, fma(s.qx, s.qx, s.qw * s.qw))));
     s.qw *= r; s.qx *= r; s.qy *= r; s.qz *= r;
   }
 }
@@ -664,7 +745,7 @@ __device__ __forceinline__ void state_propagate(FilterState& s, const V3& gyro, 
   const V3 rv = qrot({s.qw, s.qx, s.qy, s.qz}, v);
   const V3 dp{rv.x * dt, rv.y * dt, rv.z * dt};
   // dstate.chiToQuat()
-  const double n = sqrt(dchi.x * dchi.x + dchi.y * dchi.y + dchi.z * dchi.z);
+  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   Q4 dq{1, 0, 0, 0};
   const bool folded = n > chi_tol;
   if (folded) dq = qexp(dchi, n);
@@ -697,18 +778,30 @@ __device__ __forceinline__ double pick_state(const double (&x)[NS], int idx) {
 // sweep is software pipelined in tiles over both memories.
 // ------------------------------------------------------------------------------------------------
 template <int I0>
-struct HPRow0 {  // elements (I0, c), (I0+1, c), (I0+2, c) for c = 3k..3k+2 -> nine per tile, seven tiles
-  template <int T>
+struct HPRow0 {  // elements (I0, c), (I0+1, c), (I0+2, c) for c = 3B..3B+2 -> nine per tile, one tile per index triple B
+  template <int B>
   struct Tile {
     static constexpr int N = 9;
     static constexpr int row(int k) { return I0 + k % 3; }
-    static constexpr int col(int k) { return 3 * T + k / 3; }
+    static constexpr int col(int k) { return 3 * B + k / 3; }
   };
 };
 
-template <int I0>
+template <bool DC>
+__host__ __device__ constexpr int carried_block(int t) { return DC ? (t < 3 ? t + 1 : t + 2) : t; }
+template <bool DC>
+__host__ __device__ constexpr int carried_pos(int c) { return DC ? act_pos(c) : c; }
+
+// DC: only the 15 active rows/columns exist (the couplings to omega / a are exactly zero, so are their gains).
+template <int I0, bool DC>
 __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& st, int a0, long long row, long long N,
                                       long long n, long long sn, const V3& dquat, const V3& chi0) {
+  static_assert(!DC || (is_act(I0) && I0 % 3 == 0), "a DC kernel cannot update on omega / a indices");
+  constexpr int NC = DC ? N_ACT : NS;        // columns of HP that are carried
+  constexpr int NB = NC / 3;                 // index triples
+  // t-th carried triple -> its block number; column c -> its position in Y
+  constexpr auto blk = &carried_block<DC>;
+  constexpr auto pos = &carried_pos<DC>;
   // issue the measurement loads first; they are consumed after the covariance work
   double z[3], Rdg[3];
 #pragma unroll
@@ -718,29 +811,30 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
   }
   // Y starts as HP = P[idx, :]
-  double Y[3][NS];
+  double Y[3][NC];
   {
     Buf<9> b0, b1;
-    issue<typename HPRow0<I0>::template Tile<0>>(P, b0);
-    static_for<7>([&](auto tc) {
+    issue<typename HPRow0<I0>::template Tile<blk(0)>>(P, b0);
+    static_for<NB>([&](auto tc) {
       constexpr int t = tc;
       auto& cur = pick<t % 2>(b0, b1);
       auto& nxt = pick<(t + 1) % 2>(b0, b1);
-      commit<typename HPRow0<I0>::template Tile<t>>(cur);
-      if constexpr (t + 1 < 7) issue<typename HPRow0<I0>::template Tile<t + 1>>(P, nxt);
+      commit<typename HPRow0<I0>::template Tile<blk(t)>>(cur);
+      if constexpr (t + 1 < NB) issue<typename HPRow0<I0>::template Tile<blk(t + 1 < NB ? t + 1 : t)>>(P, nxt);
 #pragma unroll
       for (int k = 0; k < 9; k++) Y[k % 3][3 * t + k / 3] = cur.d[k];
     });
   }
+  constexpr int J0 = pos(I0);
   // S (symmetric) = R + P[idx, idx]
   double S00, S10, S20, S11, S21, S22;
   if (st.r_mode == 1) {
-    S00 = Rdg[0] + Y[0][I0]; S11 = Rdg[1] + Y[1][I0 + 1]; S22 = Rdg[2] + Y[2][I0 + 2];
-    S10 = Y[1][I0]; S20 = Y[2][I0]; S21 = Y[2][I0 + 1];
+    S00 = Rdg[0] + Y[0][J0]; S11 = Rdg[1] + Y[1][J0 + 1]; S22 = Rdg[2] + Y[2][J0 + 2];
+    S10 = Y[1][J0]; S20 = Y[2][J0]; S21 = Y[2][J0 + 1];
   } else {
     const double* Rm = st.R + a0 + (long long)st.m * a0;
-    S00 = __ldg(Rm) + Y[0][I0]; S11 = __ldg(Rm + st.m + 1) + Y[1][I0 + 1]; S22 = __ldg(Rm + 2 * st.m + 2) + Y[2][I0 + 2];
-    S10 = __ldg(Rm + 1) + Y[1][I0]; S20 = __ldg(Rm + 2) + Y[2][I0]; S21 = __ldg(Rm + st.m + 2) + Y[2][I0 + 1];
+    S00 = __ldg(Rm) + Y[0][J0]; S11 = __ldg(Rm + st.m + 1) + Y[1][J0 + 1]; S22 = __ldg(Rm + 2 * st.m + 2) + Y[2][J0 + 2];
+    S10 = __ldg(Rm + 1) + Y[1][J0]; S20 = __ldg(Rm + 2) + Y[2][J0]; S21 = __ldg(Rm + st.m + 2) + Y[2][J0 + 1];
   }
   // LDL^T (no pivoting; S is SPD)
   const double d0 = S00, r0 = 1.0 / d0;
@@ -751,27 +845,29 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   const double logdet = log(d0) + log(d1) + log(d2);
   // Y = L^-1 HP
 #pragma unroll
-  for (int c = 0; c < NS; c++) {
+  for (int c = 0; c < NC; c++) {
     Y[1][c] = fma(-l10, Y[0][c], Y[1][c]);
     Y[2][c] = fma(-l21, Y[1][c], fma(-l20, Y[0][c], Y[2][c]));
   }
   // covariance sweep: P[i,j] -= sum_a Y[a][i] * (Y[a][j] / d_a), packed order, tiles of RBIS_SWEEP_TILE slots
   {
     constexpr int TS = RBIS_SWEEP_TILE;
-    constexpr int NT = (NP + TS - 1) / TS;
+    constexpr int NSW = kSweepLen<DC>;
+    constexpr int NT = (NSW + TS - 1) / TS;
     Buf<TS> b0, b1;
-    issue<SlotRun<0, TS>>(P, b0);
+    issue<SweepRun<DC, 0, (NSW < TS ? NSW : TS)>>(P, b0);
     static_for<NT>([&](auto tc) {
       constexpr int t = tc;
       constexpr int s0 = t * TS;
-      constexpr int len = (NP - s0) < TS ? (NP - s0) : TS;
+      constexpr int len = (NSW - s0) < TS ? (NSW - s0) : TS;
+      using Cur = SweepRun<DC, s0, len>;
       auto& cur = pick<t % 2>(b0, b1);
       auto& nxt = pick<(t + 1) % 2>(b0, b1);
       // commit / issue on exactly the slots of the tile
-      if constexpr (any_tm<SlotRun<s0, len>>()) tm_wait_ld();
+      if constexpr (any_tm<Cur>()) tm_wait_ld();
       static_for<len>([&](auto kc) {
         constexpr int k = kc;
-        constexpr int i = row_of_slot(s0 + k), j = col_of_slot(s0 + k);
+        constexpr int i = Cur::row(k), j = Cur::col(k);
 #if RBIS_TM_PACK
         if constexpr (in_tm(i, j)) tm_settle_d(cur.d[k]);
 #else
@@ -780,10 +876,11 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
       });
       if constexpr (t + 1 < NT) {
         constexpr int s1 = s0 + TS;
-        constexpr int len1 = (NP - s1) < TS ? (NP - s1) : TS;
+        constexpr int len1 = (NSW - s1) < TS ? (NSW - s1) : TS;
+        using Nxt = SweepRun<DC, s1, len1>;
         static_for<len1>([&](auto kc) {
           constexpr int k = kc;
-          constexpr int i = row_of_slot(s1 + k), j = col_of_slot(s1 + k);
+          constexpr int i = Nxt::row(k), j = Nxt::col(k);
 #if RBIS_TM_PACK
           if constexpr (in_tm(i, j)) tm_ldd(P.tm + 2 * tm_index(i, j), nxt.d[k]);
 #else
@@ -794,8 +891,9 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
       }
       static_for<len>([&](auto kc) {
         constexpr int k = kc;
-        constexpr int i = row_of_slot(s0 + k), j = col_of_slot(s0 + k);
-        const double v = fma(-Y[0][i], Y[0][j] * r0, fma(-Y[1][i], Y[1][j] * r1, fma(-Y[2][i], Y[2][j] * r2, cur.d[k])));
+        constexpr int i = Cur::row(k), j = Cur::col(k);
+        constexpr int yi = pos(i), yj = pos(j);
+        const double v = fma(-Y[0][yi], Y[0][yj] * r0, fma(-Y[1][yi], Y[1][yj] * r1, fma(-Y[2][yi], Y[2][yj] * r2, cur.d[k])));
         P.template set<i, j>(v);
       });
       RBIS_SCHED_FENCE();
@@ -817,9 +915,12 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   // e = L^-1 r, u = D^-1 e, x += Y^T u
   const double e0 = r[0], e1 = fma(-l10, e0, r[1]), e2 = fma(-l21, e1, fma(-l20, e0, r[2]));
   const double u0 = e0 * r0, u1 = e1 * r1, u2 = e2 * r2;
-#pragma unroll
-  for (int c = 0; c < NS; c++) s.x[c] += fma(Y[0][c], u0, fma(Y[1][c], u1, Y[2][c] * u2));
-  s.ll += -logdet - (e0 * u0 + e1 * u1 + e2 * u2);
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int xc = DC ? act_col(c) : c;
+    s.x[xc] += fma(Y[0][c], u0, fma(Y[1][c], u1, Y[2][c] * u2));
+  });
+  s.ll += -logdet - fma(e2, u2, fma(e1, u1, e0 * u0));
 }
 
 // General chunk (any M <= 9, any indices): same mathematics, compact loops, run-time element access,
@@ -920,7 +1021,7 @@ __device__ __forceinline__ void meas_finish(FilterState& s, const V3& chi0, doub
                                             int renorm) {
   V3 dchi{s.x[6] - chi0.x, s.x[7] - chi0.y, s.x[8] - chi0.z};
   s.x[6] = chi0.x; s.x[7] = chi0.y; s.x[8] = chi0.z;
-  const double n = sqrt(dchi.x * dchi.x + dchi.y * dchi.y + dchi.z * dchi.z);
+  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   Q4 dq{1, 0, 0, 0};
   const bool folded = ctor_folds_chi && (n > chi_tol);
   if (folded) dq = qexp(dchi, n);
@@ -949,17 +1050,52 @@ __device__ __forceinline__ void cov_store_all(const Cov& P, double* __restrict__
   });
 }
 
+// DC variants: only the active slots live on chip
+__device__ __forceinline__ void cov_load_active(Cov& P, const double* __restrict__ src, long long stride) {
+  static_for<NP_ACT>([&](auto kc) {
+    constexpr int s_ = kAct.s[kc];
+    P.template set<row_of_slot(s_), col_of_slot(s_)>(src[(long long)s_ * stride]);
+  });
+  tm_wait_st();
+}
+__device__ __forceinline__ void cov_store_active(const Cov& P, double* __restrict__ dst, long long stride, bool active) {
+  constexpr int TILE = 12;  // 120 = 10 * 12
+  static_for<NP_ACT / TILE>([&](auto tc) {
+    constexpr int k0 = tc * TILE;
+    Buf<TILE> b;
+    issue<ActRun<k0, TILE>>(P, b);
+    commit<ActRun<k0, TILE>>(b);
+    if (active) {
+      static_for<TILE>([&](auto kc) {
+        constexpr int s_ = kAct.s[k0 + kc];
+        dst[(long long)s_ * stride] = b.d[kc];
+      });
+    }
+  });
+}
+// the (omega,omega) and (a,a) blocks as every IMU step leaves them (rbis.cpp:120-121), written to a [231][stride] array
+__device__ __forceinline__ void store_overwritten_blocks(double* __restrict__ dst, long long stride, double q_gyro, double q_accel) {
+  static_for<12>([&](auto kc) {
+    constexpr int s_ = kAct.blk[kc];
+    constexpr int i = row_of_slot(s_), j = col_of_slot(s_);
+    dst[(long long)s_ * stride] = (i != j) ? 0.0 : (j < 3 ? q_gyro : q_accel);
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused kernel: every lane loads its filter, runs the whole op program, stores it back.
 // GENERAL = false is launched when every measurement chunk of every stream is an aligned triple.
 // ------------------------------------------------------------------------------------------------
-template <bool GENERAL>
+// DC = true is launched when the host has verified that every filter's omega / a couplings are exactly zero and no
+// measurement of the program indexes omega or a (see "decoupled filters" above); it implies GENERAL = false.
+template <bool GENERAL, bool DC = false>
 __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constant__ KParams p) {
+  static_assert(!(GENERAL && DC), "the DC variant has no general measurement path");
   extern __shared__ double smem[];
   __shared__ uint32_t tm_base_s;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  // ---- tensor memory: all 512 columns; warp w owns lanes 32*(w%4).. and columns 256*(w/4).. ----
+  // ---- tensor memory: all 512 columns; warp w owns lanes 32*(w%4).. and columns TM_COLS*(w/4).. ----
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -976,12 +1112,14 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
 
   Cov P;
   P.Ps = smem + tid;
-  P.tm = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+  P.tm = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_COLS);
   FilterState s;
   static_for<NS>([&](auto i) { s.x[i] = p.vec[(long long)i * N + n]; });
   s.qw = p.quat[n]; s.qx = p.quat[N + n]; s.qy = p.quat[2 * N + n]; s.qz = p.quat[3 * N + n];
   s.ll = p.loglik[n];
-  cov_load_all(P, p.P + n, N);
+  if constexpr (DC) cov_load_active(P, p.P + n, N);
+  else cov_load_all(P, p.P + n, N);
+  bool imu_seen = false;  // DC: an IMU step ran since the (omega,omega) / (a,a) blocks in p.P were current
 
   auto load_op = [&](long long i) {
     Op o;
@@ -1047,7 +1185,8 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
       static_for<6>([&](auto k) { tm_st2(P.tm + 2 * (N_TM + 3 + k), s.x[15 + k]); });
       tm_st2(P.tm + 2 * (N_TM + 9), s.ll);
 #endif
-      cov_propagate(P, L,
+      imu_seen = true;
+      cov_propagate<DC>(P, L,
                     [&]() {
 #if RBIS_LATE_LOADS
                       load_q();
@@ -1087,13 +1226,13 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         const int a0 = st.chunk_start[ci];
         const int fast = st.chunk_fast[ci];
         switch (fast) {
-          case 0: meas3<0>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 3: meas3<3>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 6: meas3<6>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 9: meas3<9>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 12: meas3<12>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 15: meas3<15>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 18: meas3<18>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 0: if constexpr (!DC) meas3<0, false>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 3: meas3<3, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 6: meas3<6, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 9: meas3<9, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 12: if constexpr (!DC) meas3<12, false>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 15: meas3<15, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 18: meas3<18, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           default:
             if constexpr (GENERAL) {
               double xs[NS];
@@ -1117,14 +1256,41 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         d[21 * N] = s.qw; d[22 * N] = s.qx; d[23 * N] = s.qy; d[24 * N] = s.qz;
         d[25 * N] = s.ll;
       }
-      cov_store_all(P, d + 26 * N, N, active);
+      if constexpr (DC) {
+        double* dc = d + 26 * N;
+        cov_store_active(P, dc, N, active);
+        if (active) {
+          static_for<N_REST>([&](auto kc) {
+            constexpr int s_ = kAct.rest[kc];
+            dc[(long long)s_ * N] = 0.0;
+          });
+          if (imu_seen) store_overwritten_blocks(dc, N, __ldg(p.q_gyro + n), __ldg(p.q_accel + n));
+          else static_for<12>([&](auto kc) {
+            constexpr int s_ = kAct.blk[kc];
+            dc[(long long)s_ * N] = p.P[(long long)s_ * N + n];
+          });
+        }
+      } else {
+        cov_store_all(P, d + 26 * N, N, active);
+      }
     } else {
       // ---- restore from ring slot ----
       const double* d = p.snap + op.row * SNAP_ROWS * N + n;
       static_for<NS>([&](auto i) { s.x[i] = d[(long long)i * N]; });
       s.qw = d[21 * N]; s.qx = d[22 * N]; s.qy = d[23 * N]; s.qz = d[24 * N];
       s.ll = d[25 * N];
-      cov_load_all(P, d + 26 * N, N);
+      if constexpr (DC) {
+        const double* dc = d + 26 * N;
+        cov_load_active(P, dc, N);
+        // the slot's (omega,omega) / (a,a) blocks become the current ones: parked in p.P (this lane's own column)
+        if (active) static_for<12>([&](auto kc) {
+          constexpr int s_ = kAct.blk[kc];
+          p.P[(long long)s_ * N + n] = dc[(long long)s_ * N];
+        });
+        imu_seen = false;
+      } else {
+        cov_load_all(P, d + 26 * N, N);
+      }
     }
   }
 
@@ -1133,13 +1299,19 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
     p.quat[n] = s.qw; p.quat[N + n] = s.qx; p.quat[2 * N + n] = s.qy; p.quat[3 * N + n] = s.qz;
     p.loglik[n] = s.ll;
   }
-  cov_store_all(P, p.P + n, N, active);
+  if constexpr (DC) {
+    cov_store_active(P, p.P + n, N, active);
+    if (active && imu_seen) store_overwritten_blocks(p.P + n, N, __ldg(p.q_gyro + n), __ldg(p.q_accel + n));
+  } else {
+    cov_store_all(P, p.P + n, N, active);
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_base) : "memory");
 }
 
+#ifndef RBIS_FUSED_ONLY
 // ------------------------------------------------------------------------------------------------
 // layout conversion: full column-major 441 <-> packed upper 231 (both [k][N])
 // ------------------------------------------------------------------------------------------------
@@ -1155,9 +1327,21 @@ __global__ void unpack_cov_kernel(const double* __restrict__ packed, double* __r
   for (int j = 0; j < NS; j++)
     for (int i = 0; i < NS; i++) full[(long long)(i + NS * j) * N + n] = packed[(long long)slot(i, j) * N + n];
 }
+// flag[0] |= 1 when any filter has a non-zero coupling between {omega, a} and the rest (kAct.rest slots) in a
+// [231][N] packed covariance.  -0.0 counts as zero; NaN as non-zero.
+__global__ void coupling_check_kernel(const double* __restrict__ packed, long long N, int* __restrict__ flag) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool nz = false;
+  if (n < N) {
+    for (int k = 0; k < N_REST; k++) nz = nz || !(packed[(long long)c_act.rest[k] * N + n] == 0.0);
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
 __global__ void fill_kernel(double* __restrict__ dst, double v, long long count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[i] = v;
 }
+#endif  // RBIS_FUSED_ONLY
 
 }  // namespace rbisk
+#endif  // include guard (default configuration)
