@@ -41,10 +41,16 @@ BYTES_PER_STEP = 48 + 24 / 2 + (48 + 32) / 100     # IMU + leg odometry + pose r
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 # FP64 instructions the fused kernel EXECUTES per filter-step on this workload, from the ncu instruction mix
 # committed under profiles/ (r1_ncu_full_v2*_instmix.csv: warp-level DFMA / DMUL / DADD per warp-step)
-EXECUTED = {"dfma": 1640.78, "dmul": 149.64, "dadd": 143.33, "source": "profiles/r1_ncu_full_v2d_bench_instmix.csv"}
+# keyed by kernel variant (rbis_batch_last_kernel_variant): 0 dense, 2 decoupled
+EXECUTED = {0: {"dfma": 1640.78, "dmul": 149.64, "dadd": 143.33, "source": "profiles/r1_ncu_full_v2d_bench_instmix.csv"},
+            2: {"dfma": 1175.8, "dmul": 140.4, "dadd": 131.0, "source": "profiles/r1_ncu_full_v3dc_bench_instmix.csv"}}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch of this workload (65,536 filters x 200 steps), from the
 # ncu --set full capture of `bench.py --steps 3 --warmup 3` summarised in profiles/r1_ncu_full_v2d_bench_summary.csv
-NCU_TRAFFIC = {"filters": 65_536, "chunk_steps": 200, "bytes": 942.650880e6 + 88.238592e6}
+NCU_TRAFFIC = {0: {"filters": 65_536, "chunk_steps": 200, "bytes": 942.650880e6 + 88.238592e6},
+               2: {"filters": 65_536, "chunk_steps": 200, "bytes": 883.759104e6 + 88.062976e6}}  # profiles/r1_ncu_full_v3dc_bench_summary.csv
+VARIANT_NAME = {0: "dense (whole 21x21 covariance on chip, 256 filters per SM)", 1: "dense + general measurement path",
+                2: "decoupled (15x15 active block on chip, 384 filters per SM; chosen at run time because every filter's "
+                   "omega / a covariance couplings are exactly zero, bit-identical to dense)"}
 
 
 def log(*a):
@@ -64,6 +70,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--launch-groups", type=int, default=0, help="0 = library default (automatic)")
+    ap.add_argument("--dense-only", action="store_true", help="force the dense kernel variant (rbis_batch_config_t::dense_only)")
+    ap.add_argument("--no-dense-leg", action="store_true", help="skip the informational dense-variant measurement")
     return ap.parse_args()
 
 
@@ -374,7 +382,7 @@ def run_b200(args):
     def streams_of(ch):
         return [MeasStream(synth.LEGODO_IDX, ch["legodo"], R_lego), MeasStream(synth.POSE_IDX, ch["pose_z"], R_pose, quat=ch["pose_q"])]
 
-    b = RBISBatch(N, device=local, launch_groups=args.launch_groups)
+    b = RBISBatch(N, device=local, launch_groups=args.launch_groups, dense_only=args.dense_only)
     b.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
     b.set_state(vec0, quat0, cov0)
     b.synchronize()
@@ -437,6 +445,7 @@ def run_b200(args):
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     launches = b.launch_count - launches0
+    variant = b.last_kernel_variant
     total_ms = ev0.elapsed_time(end)
     kernel_ms = [ev0.elapsed_time(evk) / K]
     log(f"[rank {rank}] {K} fused launches: {ev0.elapsed_time(evk):.3f} ms = {kernel_ms[0]:.3f} ms per launch; "
@@ -450,6 +459,39 @@ def run_b200(args):
     summ = summarize(totals)
     log(f"[rank {rank}] ensemble after {n_chunks_run * Tc} steps: filters={summ['filters']} non_finite={summ['non_finite']} "
         f"mean NEES(9)={summ['mean_nees']:.3f} in-95%={summ['nees_in_95pct']:.3f} rms pos err={np.sqrt(np.mean(summ['rms_err'][9:12] ** 2)):.4f} m")
+
+    # ---- informational: the dense kernel variant on the same launches (what a coupled ensemble would get) ----
+    dense_leg = None
+    if variant == 2 and not args.no_dense_leg:
+        bd = RBISBatch(N, device=local, launch_groups=args.launch_groups, dense_only=True)
+        bd.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
+        bd.set_state(vec0, quat0, cov0)
+        sd = torch.cuda.ExternalStream(bd.cuda_stream, device=dev)
+        for c in range(W):
+            bd.run_fused(progs[c], imu=chunks[c]["imu"], streams=streams_of(chunks[c]))
+        bd.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(sd)
+        for i in range(K):
+            bd.run_fused(progs[W + i], imu=chunks[W + i]["imu"], streams=streams_of(chunks[W + i]))
+        bd.record()
+        d1.record(sd)
+        bd.synchronize()
+        torch.cuda.synchronize()
+        d_ms = d0.elapsed_time(d1) / K
+        def dev_state(h):
+            v = torch.empty((21, N), dtype=torch.float64, device=dev)
+            c = torch.empty((441, N), dtype=torch.float64, device=dev)
+            l = torch.empty((N,), dtype=torch.float64, device=dev)
+            h.get_state_into(vec=v, cov=c, loglik=l)
+            h.synchronize()
+            return v, c, l
+
+        same = all(bool(torch.equal(x, y)) for x, y in zip(dev_state(b), dev_state(bd)))
+        dense_leg = {"value": N * Tc / (d_ms * 1e-3), "unit": UNIT, "kernel_ms": d_ms, "kernel_variant": VARIANT_NAME[bd.last_kernel_variant],
+                     "bit_identical_to_headline_run": same, "this_rank_only": True}
+        log(f"[rank {rank}] dense variant on the same {K} launches: {d_ms:.3f} ms per launch, results bit-identical: {same}")
+        bd.close()
 
     # ---- e2e: host (pinned) inputs through the C ABI, results read back every step ----
     e2e = None
@@ -566,30 +608,37 @@ def run_b200(args):
     if rank == 0:
         k_ms = float(np.mean(kernel_ms))
         achieved = flops_chunk / (k_ms * 1e-3) / 1e12
+        ex = EXECUTED.get(variant)
+        tr = NCU_TRAFFIC.get(variant)
+        hw = {}
+        if ex:
+            ex_flops = 2 * ex["dfma"] + ex["dmul"] + ex["dadd"]
+            hw = {"executed_flops_per_filter_step": ex_flops,
+                  "achieved_hw": ex_flops * N * Tc / (k_ms * 1e-3) / 1e12,
+                  "frac_hw": ex_flops * N * Tc / (k_ms * 1e-3) / 1e12 / dfma_tf,
+                  "fp64_pipe_busy_frac": (ex["dfma"] + ex["dmul"] + ex["dadd"]) * 2 * N * Tc / 32 / (k_ms * 1e-3) / (148 * 4 * 1.965e9),
+                  "executed_source": ex["source"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "configs[2]: 65,536-filter ensemble per GPU, IMU 1 kHz + leg-odometry 500 Hz (m=3) + pose fix 10 Hz (m=6), fused kernel",
                        "filters_per_gpu": N, "chunk_steps": Tc, "filter_steps_per_step": world * N * Tc,
+                       "kernel_variant": VARIANT_NAME.get(variant, str(variant)),
                        "l2_policy": f"every step reads a fresh {in_bytes / 1e6:.0f} MB input chunk (> 126 MB L2); all {n_chunks_run} chunks resident in HBM",
                        "stats_allreduce": "nccl, inside the timed region" if world > 1 else "single GPU, inside the timed region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
-                         "traffic": NCU_TRAFFIC["bytes"] if (N, Tc) == (NCU_TRAFFIC["filters"], NCU_TRAFFIC["chunk_steps"]) else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic: %d input + %d state bytes" % (in_bytes, 2 * N * 8 * (231 + 26)),
+                         "traffic": tr["bytes"] if tr and (N, Tc) == (tr["filters"], tr["chunk_steps"]) else None,
+                         "traffic_unit": "bytes per launch (ncu dram read+write); algorithmic: %d input + %d state bytes" % (in_bytes, 2 * N * 8 * ((120 if variant == 2 else 231) + 26)),
                          "kernel": "rbis_fused_kernel", "kernel_ms": k_ms,
                          "kernel_ms_how": "CUDA events on the library stream around the K back-to-back fused launches (the stream joins the launch-group streams before the closing event), divided by K: launches overlap by design (launch groups), so a per-launch event pair would not bracket one launch",
                          "algorithmic_flops_per_filter_step": flops_chunk / (N * Tc),
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "nominal_peak": NOMINAL_FP64_TFLOPS, "dmma_peak_measured": dmma_tf,
                          "hbm_stream_gbs": in_bytes / (k_ms * 1e-3) / 1e9,
-                         "executed_flops_per_filter_step": 2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"],
-                         "achieved_hw": (2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * N * Tc / (k_ms * 1e-3) / 1e12,
-                         "frac_hw": (2 * EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * N * Tc / (k_ms * 1e-3) / 1e12 / dfma_tf,
-                         "fp64_pipe_busy_frac": (EXECUTED["dfma"] + EXECUTED["dmul"] + EXECUTED["dadd"]) * 2 * N * Tc / 32 / (k_ms * 1e-3) / (148 * 4 * 1.965e9),
-                         "executed_source": EXECUTED["source"],
+                         **hw,
                          "note": "achieved/frac count the dense ALGORITHMIC flops of SURVEY.md 8d (task contract); the kernel exploits the block structure of Ad and the symmetry of P and executes ~11x fewer, so frac exceeds 1. achieved_hw/frac_hw count executed flops; fp64_pipe_busy_frac = executed FP64 warp-instructions x 2 issue cycles / (SM sub-partition cycles), cf. ncu sm__pipe_fp64_cycles_active in profiles/"},
-            "cpu_baseline": cpu, "e2e": e2e, "sweep_shared_inputs": sweep, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "sweep_shared_inputs": sweep, "dense_variant": dense_leg, "gpu_launches": launches, "clocks": clocks,
             "ensemble": {"mean_nees9": summ["mean_nees"], "nees_in_95pct": summ["nees_in_95pct"], "non_finite": summ["non_finite"]},
         }
         emit(line)

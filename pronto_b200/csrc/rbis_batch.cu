@@ -23,6 +23,8 @@
 #define RBIS_PLACEMENT 2
 #undef RBIS_LATE_LOADS
 #define RBIS_LATE_LOADS 1
+#undef RBIS_PARK_STATE
+#define RBIS_PARK_STATE 2   // 168 registers per thread: the filter state waits in spare tensor memory during the sweeps
 #include "rbis_kernels.cuh"
 #undef rbisk
 #include "rbis_stats.cuh"

@@ -90,11 +90,10 @@ __host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s)
 #ifndef RBIS_PLACEMENT
 #define RBIS_PLACEMENT 1
 #endif
-#ifdef RBIS_PARK_STATE
-#define RBIS_PARK_STATE_SLOTS RBIS_PARK_STATE
-#else
-#define RBIS_PARK_STATE_SLOTS 0
-#endif
+// RBIS_PARK_STATE: 0 = the filter state stays in registers; 1 = ten state doubles are parked in spare tensor memory
+// during the covariance step; 2 = everything that a phase does not need is parked (20 doubles during the covariance
+// step, all 26 during a measurement sweep) -- for the 168-register budget of 384 filters per CTA
+#define RBIS_PARK_STATE_SLOTS (RBIS_PARK_STATE == 2 ? 26 : RBIS_PARK_STATE == 1 ? 10 : 0)
 // Which memory holds slot (i <= j):
 //   placement 0: the 15x15 active part in tensor memory, the omega/a-coupled part in shared memory;
 //   placement 1: the reverse -- the active part (5.5 accesses per slot and step, most values used by several
@@ -151,7 +150,7 @@ constexpr int N_SM = kPlace.n_sm;   // slots in shared memory
 // lane quarter split the 512 columns: TM_COLS 32-bit columns = TM_COLS/2 doubles per thread
 constexpr int TM_COLS = (512 / ((TPB + 127) / 128)) & ~1;
 static_assert(TPB % 32 == 0, "whole warps");
-static_assert(2 * (N_TM + 10 * RBIS_PARK_STATE_SLOTS) <= TM_COLS, "tensor-memory share of a thread exceeded");
+static_assert(2 * (N_TM + RBIS_PARK_STATE_SLOTS) <= TM_COLS, "tensor-memory share of a thread exceeded");
 static_assert(N_SM * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
 constexpr int SMEM_BYTES = N_SM * TPB * 8;
 
@@ -755,6 +754,36 @@ __device__ __forceinline__ void state_propagate(FilterState& s, const V3& gyro, 
   add_state_tail(s, dchi, folded, dq, chi_tol, renorm);
 }
 
+// ---- parking of the filter state in this thread's spare tensor memory (slots N_TM ...) ----
+// field k of the state: 0..20 vec, 21..24 quaternion, 25 log-likelihood; MASK selects the fields
+__device__ __forceinline__ double& state_field(FilterState& s, int k) {
+  return k < NS ? s.x[k] : k == 21 ? s.qw : k == 22 ? s.qx : k == 23 ? s.qy : k == 24 ? s.qz : s.ll;
+}
+template <uint32_t MASK>
+__device__ __forceinline__ void park_state(const Cov& P, FilterState& s) {
+  static_for<26>([&](auto kc) {
+    constexpr int k = kc;
+    if constexpr ((MASK >> k) & 1u) tm_st2(P.tm + 2 * (N_TM + k), state_field(s, k));
+  });
+}
+template <uint32_t MASK>
+__device__ __forceinline__ void unpark_state(const Cov& P, FilterState& s) {
+  uint32_t lo[26], hi[26];
+  static_for<26>([&](auto kc) {
+    constexpr int k = kc;
+    if constexpr ((MASK >> k) & 1u) tm_ld2(P.tm + 2 * (N_TM + k), lo[k], hi[k]);
+  });
+  tm_wait_ld();
+  static_for<26>([&](auto kc) {
+    constexpr int k = kc;
+    if constexpr ((MASK >> k) & 1u) state_field(s, k) = tm_settle(lo[k], hi[k]);
+  });
+}
+constexpr uint32_t PARK_ALL = (1u << 26) - 1;
+// during the covariance step: v, chi, p, b_g, b_a, quaternion, log-likelihood (omega and a are rewritten by the state
+// step that follows; the linearisation point is already in Lin)
+constexpr uint32_t PARK_COV = PARK_ALL & ~(0x7u | (0x7u << 12));
+
 // x[idx] with a runtime (warp-uniform) index: select chain, registers cannot be indexed dynamically
 __device__ __forceinline__ double pick_state(const double (&x)[NS], int idx) {
   double v = x[0];
@@ -810,6 +839,9 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
 #pragma unroll
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
   }
+#if RBIS_PARK_STATE == 2
+  park_state<PARK_ALL>(P, s);  // the sweep needs none of it; read back below
+#endif
   // Y starts as HP = P[idx, :]
   double Y[3][NC];
   {
@@ -900,6 +932,9 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
     });
   }
   tm_wait_st();
+#if RBIS_PARK_STATE == 2
+  unpark_state<PARK_ALL>(P, s);
+#endif
   // residual against the current vec (prior + earlier chunks of this update)
   double r[3];
 #pragma unroll
@@ -1089,7 +1124,11 @@ __device__ __forceinline__ void store_overwritten_blocks(double* __restrict__ ds
 // DC = true is launched when the host has verified that every filter's omega / a couplings are exactly zero and no
 // measurement of the program indexes omega or a (see "decoupled filters" above); it implies GENERAL = false.
 template <bool GENERAL, bool DC = false>
+#ifdef RBIS_MAXNREG  // dev probe: cap the registers directly instead of through the launch bounds
+__global__ void __maxnreg__(RBIS_MAXNREG) rbis_fused_kernel(const __grid_constant__ KParams p) {
+#else
 __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constant__ KParams p) {
+#endif
   static_assert(!(GENERAL && DC), "the DC variant has no general measurement path");
   extern __shared__ double smem[];
   __shared__ uint32_t tm_base_s;
@@ -1178,7 +1217,9 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         L.Rd[3] = (txy + twz) * dt;       L.Rd[4] = (1 - (txx + tzz)) * dt; L.Rd[5] = (tyz - twx) * dt;
         L.Rd[6] = (txz - twy) * dt;       L.Rd[7] = (tyz + twx) * dt;       L.Rd[8] = (1 - (txx + tyy)) * dt;
       }
-#if RBIS_PARK_STATE
+#if RBIS_PARK_STATE == 2
+      park_state<PARK_COV>(P, s);
+#elif RBIS_PARK_STATE
       // x[9..11], x[15..20] and the log-likelihood are not needed by the covariance step: parked in this thread's ten
       // spare tensor-memory slots, their 20 registers go to the column pipelines
       static_for<3>([&](auto k) { tm_st2(P.tm + 2 * (N_TM + k), s.x[9 + k]); });
@@ -1198,7 +1239,9 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
                       load_inputs();
 #endif
                     });
-#if RBIS_PARK_STATE
+#if RBIS_PARK_STATE == 2
+      unpark_state<PARK_COV>(P, s);
+#elif RBIS_PARK_STATE
       {
         Buf<10> pk;
         static_for<10>([&](auto k) { tm_ld2(P.tm + 2 * (N_TM + k), pk.lo[k], pk.hi[k]); });
