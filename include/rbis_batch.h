@@ -211,6 +211,33 @@ int rbis_planner_take(rbis_planner_t* p, rbis_op_t* out, int64_t cap, int64_t* n
  * [4] snapshots taken, [5] history entries retained. */
 int rbis_planner_counters(const rbis_planner_t* p, int64_t out[6]);
 
+/* ---- EKF smoother ("next" row 1 of SURVEY.md 8f): ekfSmoothingStep (MSE/rbis.cpp:234-266) driven as
+ * MavStateEstimator::EKFSmoothBackwardsPass (MSE/mav_state_est.cpp:98-189).  Where the reference keeps a posterior in
+ * every history node, the ensemble keeps the posteriors it wants smoothed in the snapshot ring: the forward program
+ * stores the posterior of update u into ring slot slot[u] with RBIS_OP_SNAPSHOT.
+ *
+ * rbis_smooth_plan: host-side mirror of the reference's backwards traversal over a history of n updates in history
+ * order (is_ins[u] != 0 for IMU process steps; every other update counts as a measurement, as the reset at the front
+ * of the reference's history does).  It reproduces the traversal statement by statement, including the extra
+ * decrement after trailing measurements (mav_state_est.cpp:130).  Outputs: the two slots the recursion starts from,
+ * the smoothing steps in execution (backward-in-time) order (capacity n), and alias[u] = the slot that holds update
+ * u's posterior after smoothing (the reference copies the smoothed posterior into the measurement updates that follow
+ * an IMU step, :163-169; here they alias the IMU step's slot).  Returns the number of steps, or a negative status. */
+typedef struct {
+  int32_t cur_slot;       /* posterior being smoothed: the last measurement of the time step, or the IMU step's own */
+  int32_t cur_pred_slot;  /* the IMU step's posterior of that time step (becomes the next step's prediction) */
+  int32_t out_slot;       /* where the smoothed state and covariance are written (the IMU step's slot) */
+  int32_t reserved;
+} rbis_smooth_step_t;
+int64_t rbis_smooth_plan(int64_t n, const uint8_t* is_ins, const int32_t* slot, int32_t* next_pred_slot,
+                         int32_t* next_slot, rbis_smooth_step_t* steps, int32_t* alias);
+/* Runs the steps on the device, one warp per filter (rbis_smooth.cuh); dt as passed to EKFSmoothBackwardsPass.
+ * Slots must hold snapshots; `steps` is a HOST array.  Stream-ordered like every other call. */
+int rbis_batch_smooth_backward(rbis_batch_t* h, int32_t next_pred_slot, int32_t next_slot, int64_t n_steps,
+                               const rbis_smooth_step_t* steps, double dt);
+/* Read a ring slot back: vec [21][N], quat [4][N], cov [441][N], loglik [N]; any may be NULL. */
+int rbis_batch_get_snapshot(rbis_batch_t* h, int32_t slot, double* vec, double* quat, double* cov, double* loglik, int mem);
+
 /* ---- ensemble statistics against a truth state (error definition of
  * SE/noise_id/noise_id.cpp:37-38; NEES over velocity+chi+position as roll_forward.cpp:54-57).
  * truth_vec [21] / truth_quat [4] (host) shared by all filters, or per-filter [21][N] / [4][N] (`mem`)

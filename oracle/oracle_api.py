@@ -166,20 +166,9 @@ def state_error(vec, quat, tvec, tquat):
     return out
 
 
-def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events, history_span=10_000_000,
-                 n_threads=1, trace=False):
-    """Replay an ARRIVAL-ordered event list through one MavStateEstimator per filter.
-
-    vec [21][N], quat [4][N], cov [441][N], loglik [N] (copied; results returned).
-    q_params: 4 arrays [N] or scalars.  imu [rows][6][N] or None.
-    streams: list of dicts(idx, z [rows][m][N], R (m x m shared, or [m][N] with per_filter_diag=True),
-             quat [rows][4][N] or None).
-    events: iterable of (kind, stream, row, utime, dt); kind 0 = IMU, 1 = measurement.
-    Returns dict(vec, quat, cov, loglik, calls[, trace_vec, trace_quat, trace_cov, trace_loglik])."""
-    lib = load()
+def _marshal(vec, quat, cov, q_params, imu, streams, events):
     vec, quat, cov = _a(vec).copy(), _a(quat).copy(), _a(cov).copy()
     N = vec.shape[1]
-    loglik = np.zeros(N) if loglik is None else _a(loglik).copy()
     qs = [np.full(N, float(q)) if np.isscalar(q) else _a(q, N) for q in q_params]
     ev = np.zeros(len(events), dtype=EVENT_DTYPE)
     for i, e in enumerate(events):
@@ -191,7 +180,7 @@ def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events,
         d = sarr[s]
         d.m, d.has_orient = m, int(st.get("quat") is not None)
         d.r_mode = 1 if st.get("per_filter_diag") else 0
-        d.sensor_id = int(st.get("sensor_id", 0))
+        d.sensor_id = int(st.get("sensor_id", 11))  # RBISUpdateInterface::legodo; 0 would be `ins`
         for a, i in enumerate(st["idx"]):
             d.idx[a] = int(i)
         z = _a(st["z"]); keep.append(z); d.z = z.ctypes.data
@@ -203,6 +192,22 @@ def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events,
             R = np.ascontiguousarray(np.asarray(st["R"], dtype=np.float64).reshape(m, m).T).reshape(-1)
         keep.append(R); d.R = R.ctypes.data
     imu_a = _a(imu) if imu is not None else None
+    return vec, quat, cov, N, qs, ev, sarr, keep, imu_a
+
+
+def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events, history_span=10_000_000,
+                 n_threads=1, trace=False):
+    """Replay an ARRIVAL-ordered event list through one MavStateEstimator per filter.
+
+    vec [21][N], quat [4][N], cov [441][N], loglik [N] (copied; results returned).
+    q_params: 4 arrays [N] or scalars.  imu [rows][6][N] or None.
+    streams: list of dicts(idx, z [rows][m][N], R (m x m shared, or [m][N] with per_filter_diag=True),
+             quat [rows][4][N] or None).
+    events: iterable of (kind, stream, row, utime, dt); kind 0 = IMU, 1 = measurement.
+    Returns dict(vec, quat, cov, loglik, calls[, trace_vec, trace_quat, trace_cov, trace_loglik])."""
+    lib = load()
+    vec, quat, cov, N, qs, ev, sarr, keep, imu_a = _marshal(vec, quat, cov, q_params, imu, streams, events)
+    loglik = np.zeros(N) if loglik is None else _a(loglik).copy()
     E = len(ev)
     tr = [None] * 4
     if trace:
@@ -216,6 +221,41 @@ def run_ensemble(vec, quat, cov, loglik, utime0, q_params, imu, streams, events,
     if trace:
         out.update(trace_vec=tr[0], trace_quat=tr[1], trace_cov=tr[2], trace_loglik=tr[3])
     return out
+
+
+def ekf_smoothing_step(next_pred, next, cur, dt):
+    """ekfSmoothingStep (MSE/rbis.cpp:234-266).  Each argument is (vec [21], quat [4], cov [21,21]); returns the smoothed
+    (vec, quat, cov [21,21]) of `cur`."""
+    lib = load()
+    lib.orc_ekf_smoothing_step.argtypes = [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 3
+    lib.orc_ekf_smoothing_step.restype = None
+    def cm(P):
+        return np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(21, 21).T).reshape(-1).copy()
+    npv, npq, npc = _a(next_pred[0], 21), _a(next_pred[1], 4), cm(next_pred[2])
+    nv, nq, nc = _a(next[0], 21), _a(next[1], 4), cm(next[2])
+    cv, cq, cc = _a(cur[0], 21).copy(), _a(cur[1], 4).copy(), cm(cur[2])
+    lib.orc_ekf_smoothing_step(npv.ctypes.data, npq.ctypes.data, npc.ctypes.data, nv.ctypes.data, nq.ctypes.data, nc.ctypes.data,
+                               float(dt), cv.ctypes.data, cq.ctypes.data, cc.ctypes.data)
+    return cv, cq, cc.reshape(21, 21).T.copy()
+
+
+def smooth_ensemble(vec, quat, cov, utime0, q_params, imu, streams, events, smooth_dt, n_threads=1):
+    """Forward pass as run_ensemble (in-order events, nothing truncated), then MavStateEstimator::EKFSmoothBackwardsPass
+    (MSE/mav_state_est.cpp:98-189).  Returns dict(post_vec [E][21][N], post_quat [E][4][N], post_cov [E][441][N]): every
+    update's posterior after smoothing, in history order."""
+    lib = load()
+    vp = C.c_void_p
+    lib.orc_smooth_ensemble.argtypes = [C.c_int64, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int,
+                                        C.POINTER(_Stream), C.c_int64, vp, C.c_int64, C.c_double, vp, vp, vp]
+    lib.orc_smooth_ensemble.restype = C.c_int64
+    vec, quat, cov, N, qs, ev, sarr, keep, imu_a = _marshal(vec, quat, cov, q_params, imu, streams, events)
+    E = len(ev)
+    pv, pq, pc = np.empty((E, 21, N)), np.empty((E, 4, N)), np.empty((E, 441, N))
+    lib.orc_smooth_ensemble(N, int(n_threads), vec.ctypes.data, quat.ctypes.data, cov.ctypes.data, int(utime0),
+                            qs[0].ctypes.data, qs[1].ctypes.data, qs[2].ctypes.data, qs[3].ctypes.data,
+                            imu_a.ctypes.data if imu_a is not None else None, len(streams), sarr, E, ev.ctypes.data,
+                            2_000_000_000, float(smooth_dt), pv.ctypes.data, pq.ctypes.data, pc.ctypes.data)
+    return dict(post_vec=pv, post_quat=pq, post_cov=pc)
 
 
 def noise_id_neg_loglik(vec, quat, cov, dt, q_gyro, q_accel, n_window, active=(3, 4, 5, 6, 7, 8, 9, 10, 11)):

@@ -609,6 +609,130 @@ double MavStateEstimator::getMeasurementsLogLikelihood() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// EKF smoother: rbis.cpp:234-266 and mav_state_est.cpp:98-189
+// ------------------------------------------------------------------------------------------------
+void ekfSmoothingStep(const RBIS& next_state_pred, const RBIM& next_cov_pred, const RBIS& next_state, const RBIM& next_cov,
+                      double dt, RBIS& cur_state, RBIM& cur_cov) {
+  RBIM Ac;
+  getIMUProcessLinearizationContinuous(cur_state, Ac);  // :237
+  RBIM Ad;
+  for (int c = 0; c < N; c++)
+    for (int r = 0; r < N; r++) Ad(r, c) = (r == c ? 1.0 : 0.0) + Ac(r, c) * dt;  // :238-239
+  // :243-250  zero-uncertainty biases: the 3x3 diagonal block is replaced by the identity
+  RBIM S = next_cov_pred;
+  for (int b0 : {(int)gyro_bias_ind, (int)accel_bias_ind}) {
+    bool any = false;
+    for (int k = 0; k < 3; k++) any = any || (next_cov_pred(b0 + k, b0 + k) < .00000000001);
+    if (any)
+      for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) S(b0 + r, b0 + c) = (r == c) ? 1.0 : 0.0;
+  }
+  // :253-254  L^T = S^-1 (Ad cur_cov)
+  std::vector<double> Sv(S.m, S.m + N * N), Lt(N * N);
+  for (int c = 0; c < N; c++)
+    for (int r = 0; r < N; r++) {
+      double acc = 0;
+      for (int k = 0; k < N; k++) acc += Ad(r, k) * cur_cov(k, c);
+      Lt[r + N * c] = acc;
+    }
+  LDLT ldlt(N, Sv);
+  ldlt.solveInPlace(Lt, N);
+  // :256  cur_cov += L (next_cov - next_cov_pred) L^T, L(i,k) = Lt(k,i)
+  RBIM D, T;
+  for (int i = 0; i < N * N; i++) D.m[i] = next_cov.m[i] - next_cov_pred.m[i];
+  for (int c = 0; c < N; c++)
+    for (int r = 0; r < N; r++) {
+      double acc = 0;
+      for (int k = 0; k < N; k++) acc += Lt[k + N * r] * D(k, c);
+      T(r, c) = acc;  // L * D
+    }
+  for (int c = 0; c < N; c++)
+    for (int r = 0; r < N; r++) {
+      double acc = 0;
+      for (int k = 0; k < N; k++) acc += T(r, k) * Lt[k + N * c];  // (L D) * L^T, L^T(k,c) = Lt(k,c)
+      cur_cov(r, c) += acc;
+    }
+  // :258-265
+  RBIS smooth_resid = next_state;
+  smooth_resid.subtractState(next_state_pred);
+  smooth_resid.quatToChi();
+  double innov[N];
+  for (int r = 0; r < N; r++) {
+    double acc = 0;
+    for (int k = 0; k < N; k++) acc += Lt[k + N * r] * smooth_resid.vec[k];
+    innov[r] = acc;
+  }
+  RBIS smooth_innov(innov);
+  cur_state.addState(smooth_innov);
+}
+
+// mav_state_est.cpp:98-189, statement by statement (including its iterator arithmetic: after the trailing measurements
+// have been rewound the iterator is decremented once more, :130, and `--begin()` serves as the stop mark, :139-140,
+// which on libstdc++ is the header node, i.e. end()).
+void MavStateEstimator::EKFSmoothBackwardsPass(double dt) {
+  updateHistory::historyMapIterator current_it = unprocessed_updates_start;
+  current_it--;
+  bool measurement_cur_step = false;
+  RBIS next_state;
+  RBIM next_cov;
+  RBISUpdateInterface* current_update = current_it->second;
+  while (current_update->sensor_id != RBISUpdateInterface::ins) {  // :116-124
+    current_update = current_it->second;
+    if (!measurement_cur_step) {
+      next_state = current_update->posterior_state;
+      next_cov = current_update->posterior_covariance;
+      measurement_cur_step = true;
+    }
+    current_it--;
+  }
+  RBIS next_state_pred = current_update->posterior_state;
+  RBIM next_cov_pred = current_update->posterior_covariance;
+  if (!measurement_cur_step) {
+    next_state = current_update->posterior_state;
+    next_cov = current_update->posterior_covariance;
+  }
+  current_it--;  // :130
+  RBIS cur_state, cur_state_pred;
+  RBIM cur_cov, cur_cov_pred;
+  measurement_cur_step = false;
+  updateHistory::historyMapIterator before_begin = history.updateMap.end();  // `begin()--` of the reference
+  while (before_begin != current_it) {
+    current_update = current_it->second;
+    if (current_update->sensor_id == RBISUpdateInterface::ins) {
+      cur_state_pred = current_update->posterior_state;
+      cur_cov_pred = current_update->posterior_covariance;
+      if (!measurement_cur_step) {
+        cur_state = cur_state_pred;
+        cur_cov = cur_cov_pred;
+      }
+      ekfSmoothingStep(next_state_pred, next_cov_pred, next_state, next_cov, dt, cur_state, cur_cov);
+      current_update->posterior_covariance = cur_cov;
+      current_update->posterior_state = cur_state;
+      updateHistory::historyMapIterator forward_it = current_it;
+      forward_it++;
+      while (forward_it->second->sensor_id != RBISUpdateInterface::ins) {  // :165-169
+        forward_it->second->posterior_state = current_update->posterior_state;
+        forward_it->second->posterior_covariance = current_update->posterior_covariance;
+        forward_it++;
+      }
+      next_state = cur_state;
+      next_cov = cur_cov;
+      next_state_pred = cur_state_pred;
+      next_cov_pred = cur_cov_pred;
+      measurement_cur_step = false;
+    } else {
+      if (!measurement_cur_step) {
+        cur_state = current_update->posterior_state;
+        cur_cov = current_update->posterior_covariance;
+        measurement_cur_step = true;
+      }
+    }
+    if (current_it == history.updateMap.begin()) current_it = history.updateMap.end();  // `--begin()`
+    else current_it--;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // noise identification, state-estimator/src/noise_id/noise_id.cpp:9-65
 // ------------------------------------------------------------------------------------------------
 void sampleProcessForward(const std::vector<RBIS>& truth_state_history, const std::vector<RBIM>& truth_cov_history, double dt,

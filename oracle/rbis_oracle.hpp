@@ -106,6 +106,9 @@ double indexedPlusOrientationMeasurement(int m, const double* z, const Quat& qua
                                          RBIS& dstate, RBIM& dcov);
 void rbisApplyDelta(const RBIS& prior_state, const RBIM& prior_cov, const RBIS& dstate, const RBIM& dcov,
                     RBIS& posterior_state, RBIM& posterior_cov);
+// EKF / RTS smoothing step, rbis.cpp:234-266 ("next" row 1 of SURVEY.md 8f)
+void ekfSmoothingStep(const RBIS& next_state_pred, const RBIM& next_cov_pred, const RBIS& next_state, const RBIM& next_cov,
+                      double dt, RBIS& cur_state, RBIM& cur_cov);
 
 // ---- IMU-noise identification, state-estimator/src/noise_id/noise_id.cpp:9-65 ("next" row 2 of SURVEY.md 8f) ----
 // sampleProcessForward: windows of N_window IMU steps rolled forward from the truth history with TWO covariance
@@ -195,6 +198,7 @@ class MavStateEstimator {
   void addUpdate(RBISUpdateInterface* update, bool roll_forward);
   void getHeadState(RBIS& head_state, RBIM& head_cov);
   double getMeasurementsLogLikelihood();
+  void EKFSmoothBackwardsPass(double dt);  // mav_state_est.cpp:98-189
 };
 
 }  // namespace rbis_oracle

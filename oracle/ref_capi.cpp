@@ -103,11 +103,12 @@ typedef struct {
   double dt;
 } orc_event_t;
 
-int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, double* cov, double* loglik, int64_t utime0,
+static int64_t run_ensemble_impl(int64_t Nf, int n_threads, double* vec, double* quat, double* cov, double* loglik, int64_t utime0,
                          const double* q_gyro, const double* q_accel, const double* q_gyro_bias, const double* q_accel_bias,
                          const double* imu, int n_streams, const orc_stream_t* streams, int64_t n_events,
                          const orc_event_t* events, int64_t history_span, double* trace_vec, double* trace_quat,
-                         double* trace_cov, double* trace_loglik) {
+                         double* trace_cov, double* trace_loglik, double smooth_dt,
+                         double* post_vec, double* post_quat, double* post_cov) {
   (void)n_streams;
   rbis_ref_shim_history_span = history_span;
   std::atomic<int64_t> next(0);
@@ -166,6 +167,20 @@ int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, d
           if (trace_loglik) trace_loglik[e * Nf + n] = ll0 + est.getMeasurementsLogLikelihood();
         }
       }
+      if (smooth_dt > 0) {  // mav_state_est.cpp:98-189, then every update's posterior in history order (reset excluded)
+        est.EKFSmoothBackwardsPass(smooth_dt);
+        int64_t e = -1;
+        for (auto& kv : est.history.updateMap) {
+          if (e >= 0) {
+            double pv[21], pq[4];
+            putState(kv.second->posterior_state, pv, pq);
+            for (int i = 0; i < 21; i++) post_vec[(e * 21 + i) * Nf + n] = pv[i];
+            for (int i = 0; i < 4; i++) post_quat[(e * 4 + i) * Nf + n] = pq[i];
+            for (int i = 0; i < 441; i++) post_cov[((int64_t)e * 441 + i) * Nf + n] = kv.second->posterior_covariance.data()[i];
+          }
+          e++;
+        }
+      }
       RBIS hs;
       RBIM hP;
       est.getHeadState(hs, hP);
@@ -185,6 +200,38 @@ int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, d
     for (auto& t : th) t.join();
   }
   return -1;
+}
+
+int64_t orc_run_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, double* cov, double* loglik, int64_t utime0,
+                         const double* q_gyro, const double* q_accel, const double* q_gyro_bias, const double* q_accel_bias,
+                         const double* imu, int n_streams, const orc_stream_t* streams, int64_t n_events,
+                         const orc_event_t* events, int64_t history_span, double* trace_vec, double* trace_quat,
+                         double* trace_cov, double* trace_loglik) {
+  return run_ensemble_impl(Nf, n_threads, vec, quat, cov, loglik, utime0, q_gyro, q_accel, q_gyro_bias, q_accel_bias, imu,
+                           n_streams, streams, n_events, events, history_span, trace_vec, trace_quat, trace_cov, trace_loglik,
+                           0.0, nullptr, nullptr, nullptr);
+}
+
+// Forward pass as orc_run_ensemble, then MavStateEstimator::EKFSmoothBackwardsPass(smooth_dt) (mav_state_est.cpp:98-189);
+// post_* [E][k][N] receive every update's posterior AFTER smoothing, in history order.  history_span must keep everything.
+int64_t orc_smooth_ensemble(int64_t Nf, int n_threads, double* vec, double* quat, double* cov, int64_t utime0,
+                            const double* q_gyro, const double* q_accel, const double* q_gyro_bias, const double* q_accel_bias,
+                            const double* imu, int n_streams, const orc_stream_t* streams, int64_t n_events,
+                            const orc_event_t* events, int64_t history_span, double smooth_dt, double* post_vec,
+                            double* post_quat, double* post_cov) {
+  return run_ensemble_impl(Nf, n_threads, vec, quat, cov, nullptr, utime0, q_gyro, q_accel, q_gyro_bias, q_accel_bias, imu,
+                           n_streams, streams, n_events, events, history_span, nullptr, nullptr, nullptr, nullptr, smooth_dt,
+                           post_vec, post_quat, post_cov);
+}
+
+// rbis.cpp:234-266 on one filter; cur_* are updated in place
+void orc_ekf_smoothing_step(const double* np_vec, const double* np_quat, const double* np_cov, const double* n_vec,
+                            const double* n_quat, const double* n_cov, double dt, double* c_vec, double* c_quat, double* c_cov) {
+  RBIS cur = makeState(c_vec, c_quat);
+  RBIM P = getCov(c_cov);
+  ekfSmoothingStep(makeState(np_vec, np_quat), getCov(np_cov), makeState(n_vec, n_quat), getCov(n_cov), dt, cur, P);
+  putState(cur, c_vec, c_quat);
+  putCov(P, c_cov);
 }
 
 }  // extern "C"

@@ -136,6 +136,22 @@ class RBISBatch:
         capi.check(self.lib.rbis_batch_get_state(self.h, pv, pq, pc, pl, C.byref(ut), mem))
         return ut.value
 
+    def get_snapshot(self, slot, cov=True):
+        """Ring slot -> (vec [21][N], quat [4][N], cov [441][N] or None, loglik [N]) as numpy."""
+        N = self.N
+        vec = np.empty((21, N)); quat = np.empty((4, N)); ll = np.empty(N)
+        P = np.empty((441, N)) if cov else None
+        capi.check(self.lib.rbis_batch_get_snapshot(self.h, int(slot), vec.ctypes.data, quat.ctypes.data,
+                                                    P.ctypes.data if cov else None, ll.ctypes.data, capi.MEM_HOST))
+        return vec, quat, P, ll
+
+    def smooth_backward(self, next_pred_slot, next_slot, steps, dt):
+        """rbis_batch_smooth_backward; steps: structured array of smoother.STEP_DTYPE in execution order."""
+        steps = np.ascontiguousarray(steps)
+        assert steps.dtype.itemsize == 16
+        capi.check(self.lib.rbis_batch_smooth_backward(self.h, int(next_pred_slot), int(next_slot), len(steps),
+                                                       steps.ctypes.data, float(dt)))
+
     def set_filter(self, n, vec, quat, cov, loglik=0.0):
         vec = np.ascontiguousarray(vec, dtype=np.float64); quat = np.ascontiguousarray(quat, dtype=np.float64)
         cov = np.ascontiguousarray(cov, dtype=np.float64)

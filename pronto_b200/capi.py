@@ -73,6 +73,9 @@ PROTOTYPES = {
     "rbis_batch_stream": (C.c_void_p, [C.c_void_p]),
     "rbis_batch_launch_count": (C.c_int64, [C.c_void_p]),
     "rbis_batch_last_kernel_variant": (C.c_int, [C.c_void_p]),
+    "rbis_smooth_plan": (C.c_int64, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rbis_batch_smooth_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_double]),
+    "rbis_batch_get_snapshot": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "rbis_batch_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "rbis_batch_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),
     "rbis_batch_set_filter": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),

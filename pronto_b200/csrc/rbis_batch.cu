@@ -28,6 +28,7 @@
 #include "rbis_kernels.cuh"
 #undef rbisk
 #include "rbis_stats.cuh"
+#include "rbis_smooth.cuh"
 static_assert(sizeof(rbisk::KParams) == sizeof(rbisk_dc::KParams), "both kernel configurations take the same parameter block");
 
 namespace {
@@ -236,8 +237,20 @@ int copy_in(rbis_batch* h, DevBuf& buf, const double* src, size_t count, int mem
   return 0;
 }
 
+int validate_stream(int s, const rbis_stream_t& in) {
+  if (in.m < 1 || in.m > RBIS_MAX_MEAS) return fail(RBIS_ERR_INVALID, "stream %d: m=%d out of range", s, in.m);
+  for (int a = 0; a < in.m; a++)
+    if (in.idx[a] < 0 || in.idx[a] >= RBIS_NUM_STATES) return fail(RBIS_ERR_INVALID, "stream %d: index %d out of range", s, in.idx[a]);
+  if (in.rows < 0) return fail(RBIS_ERR_INVALID, "stream %d: negative rows", s);
+  if (in.rows > 0 && (!in.z || !in.R)) return fail(RBIS_ERR_INVALID, "stream %d: z and R are required", s);
+  if (in.has_orientation && in.rows > 0 && !in.quat) return fail(RBIS_ERR_INVALID, "stream %d: has_orientation but quat is NULL", s);
+  if (in.r_mode != RBIS_R_SHARED_FULL && in.r_mode != RBIS_R_PER_FILTER_DIAG) return fail(RBIS_ERR_INVALID, "stream %d: bad r_mode", s);
+  return 0;
+}
+
+// dry_run: validate the whole call (ops, streams) and return without enqueueing anything
 int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
-                 int n_streams, const rbis_stream_t* streams, int mem, bool use_maps = true) {
+                 int n_streams, const rbis_stream_t* streams, int mem, bool use_maps = true, bool dry_run = false) {
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(RBIS_ERR_INVALID, "bad op list");
   if (n_streams < 0 || n_streams > RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "n_streams out of range");
@@ -287,6 +300,12 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     }
   }
 
+  if (dry_run) {
+    for (int s = 0; s < n_streams; s++)
+      if (int rc = validate_stream(s, streams[s])) return rc;
+    return 0;
+  }
+
   rbisk::KParams kp;
   std::memset(&kp, 0, sizeof(kp));
   kp.N = N;
@@ -328,13 +347,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
     rbisk::StreamDesc& d = kp.streams[s];
-    if (in.m < 1 || in.m > RBIS_MAX_MEAS) return fail(RBIS_ERR_INVALID, "stream %d: m=%d out of range", s, in.m);
-    for (int a = 0; a < in.m; a++)
-      if (in.idx[a] < 0 || in.idx[a] >= RBIS_NUM_STATES) return fail(RBIS_ERR_INVALID, "stream %d: index %d out of range", s, in.idx[a]);
-    if (in.rows < 0) return fail(RBIS_ERR_INVALID, "stream %d: negative rows", s);
-    if (in.rows > 0 && (!in.z || !in.R)) return fail(RBIS_ERR_INVALID, "stream %d: z and R are required", s);
-    if (in.has_orientation && in.rows > 0 && !in.quat) return fail(RBIS_ERR_INVALID, "stream %d: has_orientation but quat is NULL", s);
-    if (in.r_mode != RBIS_R_SHARED_FULL && in.r_mode != RBIS_R_PER_FILTER_DIAG) return fail(RBIS_ERR_INVALID, "stream %d: bad r_mode", s);
+    if (int rc = validate_stream(s, in)) return rc;
     d.m = in.m; d.has_orient = in.has_orientation ? 1 : 0; d.r_mode = in.r_mode;
     for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
     d.map = use_maps ? h->d_map[1 + s] : nullptr;
@@ -555,6 +568,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     h->snap_dc.assign((size_t)c.snapshot_slots, 0);
   }
   CREATE_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rbisk::SMOOTH_SMEM_BYTES));
   CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -779,6 +793,20 @@ int rbis_batch_set_column_map(rbis_batch_t* h, int which, const int32_t* map, in
 int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
                          int n_streams, const rbis_stream_t* streams, int mem) {
   if (n_streams > 0 && !streams) return fail(RBIS_ERR_INVALID, "streams is NULL");
+  // A long program over device-resident inputs is cut into consecutive pieces (same arrays, absolute rows): with launch
+  // groups the pieces overlap like consecutive calls do, so the partially filled last wave of CTAs of one piece runs
+  // beside the next piece instead of idling most SMs for the whole program.  The state round trip through HBM per
+  // piece is ~150 MB per 65,536 filters, noise against a few hundred ops of work.
+  constexpr int64_t kPieceOps = 256;
+  if (h && h->n_groups > 1 && mem == RBIS_MEM_DEVICE && ops && n_ops >= 2 * kPieceOps) {
+    if (int rc = launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem, true, /*dry_run=*/true)) return rc;
+    const int64_t pieces = (n_ops + kPieceOps - 1) / kPieceOps;
+    for (int64_t k = 0; k < pieces; k++) {
+      const int64_t o0 = n_ops * k / pieces, o1 = n_ops * (k + 1) / pieces;
+      if (int rc = launch_fused(h, o1 - o0, ops + o0, imu, imu_rows, n_streams, streams, mem)) return rc;
+    }
+    return 0;
+  }
   return launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem);
 }
 
@@ -994,6 +1022,66 @@ int rbis_measure_fp64_peak(int device, int iters, double* dfma_tflops, double* d
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(d_out);
+  return 0;
+}
+
+int rbis_batch_smooth_backward(rbis_batch_t* h, int32_t next_pred_slot, int32_t next_slot, int64_t n_steps,
+                               const rbis_smooth_step_t* steps, double dt) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (n_steps < 0 || (n_steps > 0 && !steps)) return fail(RBIS_ERR_INVALID, "bad step list");
+  if (!(dt > 0)) return fail(RBIS_ERR_INVALID, "dt must be positive");
+  const int S = h->cfg.snapshot_slots;
+  auto ok = [&](int32_t s) { return s >= 0 && s < S && h->snap_valid[(size_t)s]; };
+  if (!ok(next_pred_slot) || !ok(next_slot)) return fail(RBIS_ERR_STATE, "start slots %d / %d are out of range or empty", next_pred_slot, next_slot);
+  for (int64_t i = 0; i < n_steps; i++)
+    if (!ok(steps[i].cur_slot) || !ok(steps[i].cur_pred_slot) || steps[i].out_slot < 0 || steps[i].out_slot >= S)
+      return fail(RBIS_ERR_STATE, "smoothing step %lld names an out-of-range or empty snapshot slot", (long long)i);
+  if (n_steps == 0) return 0;
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  static_assert(sizeof(rbis_smooth_step_t) == sizeof(rbisk::SmoothStep), "step layout");
+  const size_t n_dbl = ((size_t)n_steps * sizeof(rbisk::SmoothStep) + 7) / 8;
+  if (h->misc.ensure(n_dbl)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  CUDA_TRY(cudaMemcpyAsync(h->misc.p, steps, (size_t)n_steps * sizeof(rbisk::SmoothStep), cudaMemcpyHostToDevice, h->stream));
+  const unsigned grid = (unsigned)((h->N + rbisk::SMOOTH_WARPS - 1) / rbisk::SMOOTH_WARPS);
+  rbisk::rbis_smooth_kernel<<<grid, rbisk::SMOOTH_WARPS * 32, rbisk::SMOOTH_SMEM_BYTES, h->stream>>>(
+      h->snap, (long long)h->N, next_pred_slot, next_slot, reinterpret_cast<const rbisk::SmoothStep*>(h->misc.p), (long long)n_steps,
+      dt, h->cfg.g_val, h->cfg.chi_tol, h->cfg.ctor_folds_chi);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  for (int64_t i = 0; i < n_steps; i++) {
+    h->snap_valid[(size_t)steps[i].out_slot] = 1;
+    h->snap_dc[(size_t)steps[i].out_slot] = 0;  // smoothed covariances carry no structural zeros
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // `steps` scratch and the caller's array are free again
+  return 0;
+}
+
+int rbis_batch_get_snapshot(rbis_batch_t* h, int32_t slot, double* vec, double* quat, double* cov, double* loglik, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (slot < 0 || slot >= h->cfg.snapshot_slots) return fail(RBIS_ERR_INVALID, "snapshot slot %d out of range", slot);
+  if (!h->snap_valid[(size_t)slot]) return fail(RBIS_ERR_STATE, "snapshot slot %d is empty", slot);
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  const size_t N = (size_t)h->N;
+  const double* base = h->snap + (size_t)slot * rbisk::SNAP_ROWS * N;
+  const cudaMemcpyKind kind = mem == RBIS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (vec) CUDA_TRY(cudaMemcpyAsync(vec, base, N * 21 * sizeof(double), kind, h->stream));
+  if (quat) CUDA_TRY(cudaMemcpyAsync(quat, base + 21 * N, N * 4 * sizeof(double), kind, h->stream));
+  if (loglik) CUDA_TRY(cudaMemcpyAsync(loglik, base + 25 * N, N * sizeof(double), kind, h->stream));
+  if (cov) {
+    double* dst = cov;
+    if (mem == RBIS_MEM_HOST) {
+      if (h->full_cov.ensure(N * 441)) return fail(RBIS_ERR_ALLOC, "covariance scratch allocation failed");
+      dst = h->full_cov.p;
+    }
+    rbisk::unpack_cov_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(base + 26 * N, dst, (long long)N);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(cov, dst, N * 441 * sizeof(double), kind, h->stream));
+  }
+  if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

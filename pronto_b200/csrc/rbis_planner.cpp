@@ -210,4 +210,57 @@ int rbis_planner_counters(const rbis_planner_t* p, int64_t out[6]) {
   return 0;
 }
 
+// EKFSmoothBackwardsPass's traversal on indices (mav_state_est.cpp:98-189): `it` plays current_it, -1 plays the
+// `--begin()` stop mark.
+int64_t rbis_smooth_plan(int64_t n, const uint8_t* is_ins, const int32_t* slot, int32_t* next_pred_slot, int32_t* next_slot,
+                         rbis_smooth_step_t* steps, int32_t* alias) {
+  if (n <= 0 || !is_ins || !slot || !next_pred_slot || !next_slot || !steps || !alias)
+    return rbis_set_error(RBIS_ERR_INVALID, "null argument or empty history");
+  bool any_ins = false;
+  for (int64_t u = 0; u < n; u++) {
+    alias[u] = slot[u];
+    any_ins = any_ins || is_ins[u];
+  }
+  if (!any_ins) return rbis_set_error(RBIS_ERR_STATE, "history holds no IMU process step");
+  int64_t it = n - 1;  // :108-109  latest processed update
+  bool measurement_cur_step = false;
+  int64_t next = -1;
+  int64_t cu = it;
+  while (!is_ins[cu]) {  // :116-124  rewind through the trailing measurements
+    cu = it;
+    if (!measurement_cur_step) {
+      next = cu;
+      measurement_cur_step = true;
+    }
+    it--;
+  }
+  const int64_t next_pred = cu;  // :126-127
+  if (!measurement_cur_step) next = cu;
+  it--;  // :130
+  *next_pred_slot = slot[next_pred];
+  *next_slot = slot[next];
+  measurement_cur_step = false;
+  int64_t cur = -1, n_steps = 0;
+  while (it >= 0) {  // :141-187 (it < -1 can only follow the extra decrement on a two-entry history)
+    cu = it;
+    if (is_ins[cu]) {
+      if (!measurement_cur_step) cur = cu;
+      rbis_smooth_step_t st;
+      st.cur_slot = slot[cur];
+      st.cur_pred_slot = slot[cu];
+      st.out_slot = slot[cu];
+      st.reserved = 0;
+      steps[n_steps++] = st;
+      // :163-169  the measurement updates that follow this IMU step take the smoothed posterior
+      for (int64_t f = cu + 1; f < n && !is_ins[f]; f++) alias[f] = slot[cu];
+      measurement_cur_step = false;
+    } else if (!measurement_cur_step) {
+      cur = cu;
+      measurement_cur_step = true;
+    }
+    it--;
+  }
+  return n_steps;
+}
+
 }  // extern "C"
