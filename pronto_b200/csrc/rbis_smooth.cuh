@@ -29,9 +29,9 @@ struct SmoothStep {
 
 constexpr int SM_LD = NS;                      // leading dimension of the shared 21x21 matrices
 constexpr int SM_MAT = NS * NS;                // 441
-constexpr int SM_WARP_DOUBLES = 5 * SM_MAT + 4 * 26 + 24;  // Sf, Dm, G, Pp, Pn + 4 states + innovation  = 2,333
+constexpr int SM_WARP_DOUBLES = 5 * SM_MAT + 4 * 26 + 2 * NS + 1;  // Sf, Dm, G, Pp, Pn + 4 states + innovation + 1/d = 2,352
 constexpr int SMOOTH_WARPS = 4;
-constexpr int SMOOTH_SMEM_BYTES = SMOOTH_WARPS * SM_WARP_DOUBLES * 8;  // 74,656 B per CTA, three CTAs per SM
+constexpr int SMOOTH_SMEM_BYTES = SMOOTH_WARPS * SM_WARP_DOUBLES * 8;  // 75,264 B per CTA, three CTAs per SM
 
 // state record in shared memory: 21 vec, 4 quat (w,x,y,z), 1 loglik
 __device__ __forceinline__ void load_state_rec(const double* __restrict__ slot_base, long long N, int lane, double* rec) {
@@ -57,6 +57,7 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
   double* st_c = st_n + 26;     // cur_state
   double* st_cp = st_c + 26;    // cur_state_pred
   double* innov = st_cp + 26;
+  double* rdiag = innov + NS;  // 1 / d_k of the factorisation
 
   auto slot_ptr = [&](int s) { return snap + (long long)s * SNAP_ROWS * N + n; };
   // column j of the symmetric packed covariance of a ring slot
@@ -95,6 +96,7 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
     if (!same) load_col(stp.cur_pred_slot, ccp);
     load_state_rec(slot_ptr(stp.cur_slot), N, lane, st_c);
     load_state_rec(slot_ptr(stp.cur_pred_slot), N, lane, st_cp);
+    double sc[NS];  // column j of S (rows >= j are the ones the factorisation uses)
 #pragma unroll
     for (int i = 0; i < NS; i++) {
       const double pp = Pp[i + SM_LD * j];
@@ -102,32 +104,33 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
       double s = pp;
       if (fix_g && i >= 15 && i < 18 && j >= 15 && j < 18) s = (i == j) ? 1.0 : 0.0;
       if (fix_a && i >= 18 && j >= 18) s = (i == j) ? 1.0 : 0.0;
-      Sf[i + SM_LD * j] = s;
+      sc[i] = s;
     }
     __syncwarp();
     // next_cov_pred of the NEXT step = this step's cur_cov_pred (mav_state_est.cpp:175)
 #pragma unroll
     for (int i = 0; i < NS; i++) Pp[i + SM_LD * j] = same ? ccur[i] : ccp[i];
-    // ---- LDL^T of S in place (lower triangle; unit L below the diagonal, D on it), no pivoting ----
-    for (int k = 0; k < NS; k++) {
-      const double d = Sf[k * (SM_LD + 1)];
-      const double rd = 1.0 / d;
-      double ljk = 0.0;
-      if (j > k) {
-        ljk = Sf[j + SM_LD * k] * rd;
+    // ---- LDL^T of S, no pivoting: lane j keeps column j in registers; at step k lane k publishes its scaled column
+    // (unit L below the diagonal of Sf, 1/d_k in rdiag) and the lanes right of it take their rank-1 update ----
+    static_for<NS>([&](auto kc) {
+      constexpr int k = kc;
+      if (lane == k) {
+        const double rd = 1.0 / sc[k];
+        rdiag[k] = rd;
+        Sf[k * (SM_LD + 1)] = sc[k];
+#pragma unroll
+        for (int i = k + 1; i < NS; i++) Sf[i + SM_LD * k] = sc[i] * rd;
       }
       __syncwarp();
-      if (j > k && on) Sf[j + SM_LD * k] = ljk;
-      __syncwarp();
-      if (j > k) {
-        const double f = ljk * d;
-        for (int i = j; i < NS; i++) {
-          const double v = fma(-Sf[i + SM_LD * k], f, Sf[i + SM_LD * j]);
-          if (on) Sf[i + SM_LD * j] = v;
+      if constexpr (k + 1 < NS) {
+        if (j > k) {
+          const double f = Sf[j + SM_LD * k] * Sf[k * (SM_LD + 1)];  // l_jk d_k
+#pragma unroll
+          for (int i = k + 1; i < NS; i++)
+            if (i >= j) sc[i] = fma(-Sf[i + SM_LD * k], f, sc[i]);
         }
       }
-      __syncwarp();
-    }
+    });
     // ---- M[:,j] = Ad cur_cov[:,j], Ad = I + dt Ac at cur_state (rbis.cpp:236-239, 12-35) ----
     double m[NS];
     {
@@ -151,22 +154,22 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
       m[9] = fma(dt, r.x, ccur[9]); m[10] = fma(dt, r.y, ccur[10]); m[11] = fma(dt, r.z, ccur[11]);
     }
     // ---- G[:,j] = S^-1 M[:,j]: forward, diagonal, backward substitution against the shared factor ----
+    // column-oriented, so that the 20 updates of a stage are independent; the warp barriers are there for ptxas, which
+    // otherwise hoists the loads of the WHOLE factor (210 doubles) to the top and spills them
+    static_for<NS - 1>([&](auto kc) {
+      constexpr int k = kc;
 #pragma unroll
-    for (int i = 1; i < NS; i++) {
-      double acc = m[i];
+      for (int i = k + 1; i < NS; i++) m[i] = fma(-Sf[i + SM_LD * k], m[k], m[i]);
+      __syncwarp();
+    });
 #pragma unroll
-      for (int k = 0; k < i; k++) acc = fma(-Sf[i + SM_LD * k], m[k], acc);
-      m[i] = acc;
-    }
+    for (int i = 0; i < NS; i++) m[i] *= rdiag[i];
+    static_for<NS - 1>([&](auto kc) {
+      constexpr int k = NS - 1 - kc;
 #pragma unroll
-    for (int i = 0; i < NS; i++) m[i] = m[i] / Sf[i * (SM_LD + 1)];
-#pragma unroll
-    for (int i = NS - 2; i >= 0; i--) {
-      double acc = m[i];
-#pragma unroll
-      for (int k = i + 1; k < NS; k++) acc = fma(-Sf[k + SM_LD * i], m[k], acc);
-      m[i] = acc;
-    }
+      for (int i = 0; i < k; i++) m[i] = fma(-Sf[k + SM_LD * i], m[k], m[i]);
+      __syncwarp();
+    });
     if (on) {
 #pragma unroll
       for (int i = 0; i < NS; i++) G[i + SM_LD * j] = m[i];
@@ -195,6 +198,7 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
 #pragma unroll
       for (int k = 0; k < NS; k++) acc = fma(Dm[i + SM_LD * k], m[k], acc);
       wv[i] = acc;
+      if (i % 3 == 2) __syncwarp();
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -202,6 +206,7 @@ rbis_smooth_kernel(double* __restrict__ snap, long long N, int next_pred_slot, i
 #pragma unroll
       for (int k = 0; k < NS; k++) acc = fma(G[k + SM_LD * i], wv[k], acc);
       ccur[i] += acc;
+      if (i % 3 == 2) __syncwarp();
     }
     // ---- cur_state.addState(RBIS(L resid))  (rbis.cpp:263-265); every lane carries the same state ----
     FilterState s;
