@@ -430,6 +430,24 @@ class LegOdoCommon {
   }
 };
 
+// MavStateEstimator::EKFSmoothBackwardsPass (MSE/mav_state_est.cpp:98-189) for an ensemble whose forward program stored
+// the posterior of history entry u (entry 0 = the reset, is_ins[u] for IMU process steps) in snapshot slot slot[u].
+// Plans the reference's backwards traversal on the host (rbis_smooth_plan) and runs ekfSmoothingStep
+// (MSE/rbis.cpp:234-266) for every filter on the device.  Returns, per history entry, the slot that now holds its
+// smoothed posterior (the reference copies the smoothed posterior of an IMU step into the measurement updates that
+// follow it; here they alias its slot) -- read with rbis_batch_get_snapshot.
+inline std::vector<int32_t> EKFSmoothBackwardsPass(RBISEnsemble& filters, const std::vector<uint8_t>& is_ins,
+                                                   const std::vector<int32_t>& slot, double dt) {
+  if (is_ins.size() != slot.size() || is_ins.empty()) throw Error(RBIS_ERR_INVALID, "EKFSmoothBackwardsPass: bad history description");
+  std::vector<rbis_smooth_step_t> steps(is_ins.size());
+  std::vector<int32_t> alias(is_ins.size());
+  int32_t next_pred = 0, next = 0;
+  const int64_t n_steps = rbis_smooth_plan((int64_t)is_ins.size(), is_ins.data(), slot.data(), &next_pred, &next, steps.data(), alias.data());
+  if (n_steps < 0) check((int)n_steps);
+  check(rbis_batch_smooth_backward(filters.handle(), next_pred, next, n_steps, steps.data(), dt));
+  return alias;
+}
+
 }  // namespace batch
 }  // namespace MavStateEst
 

@@ -1,6 +1,6 @@
 """ctypes face of the CPU ORACLE (oracle/_build/librbis_oracle.so).
 
-Test infrastructure only (PARITY UNPINNED, see rbis_oracle.hpp): imported by tests/,
+Test infrastructure only (how its parity is pinned: see rbis_oracle.hpp): imported by tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by pronto_b200.
 """
 import ctypes as C

@@ -5,13 +5,14 @@
 // bench.py has a CPU baseline to time.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may link or call anything in oracle/.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path, and its
-// arithmetic depends on Eigen 3 and MIT's eigen_utils pod (pkg-config `eigen-utils`, no version
-// pin anywhere: state-estimator/src/mav_state_est/CMakeLists.txt:15), neither of which is under
-// /root/reference or installed in this image, so the reference cannot be compiled here
-// (oracle/_ref is therefore empty).  The oracle follows the reference's own sources line by line
-// and restates the eigen_utils / Eigen semantics it leans on as tabulated in SURVEY.md section 8c;
-// the two constants that cannot be checked in-repo (G_VAL, CHI_TOL) are runtime-settable.
+// PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path.  The oracle is pinned against the
+// reference's OWN sources instead: oracle/Makefile (`make ref`) compiles the unmodified rbis.cpp,
+// rbis_update_interface.cpp, update_history.cpp and mav_state_est.cpp from /root/reference into oracle/_ref/librbis_ref.so
+// against stand-in headers (oracle/ref_shim/) for the absent Eigen 3 / eigen_utils / LCM / libbot, and
+// tests/test_ref_pins_oracle.py + tests/test_smoother.py hold oracle == reference to 1e-12.  What stays RESTATED (and is
+// therefore "parity unpinned" in the strict sense) is the inside of eigen_utils: RigidBodyState's algebra, g_val and the
+// chiToQuat tolerance follow SURVEY.md section 8c in both the stand-in headers and this file; the two constants that
+// cannot be checked in-repo (G_VAL, CHI_TOL) are runtime-settable.
 //
 // Reference files followed (all under /root/reference/state-estimator/src/mav_state_est/):
 //   rbis.hpp:19-146                   types and API names
@@ -19,6 +20,7 @@
 //   rbis_update_interface.hpp:8-120   update objects
 //   rbis_update_interface.cpp:23-107  updateFilter bodies, log-likelihood bookkeeping
 //   mav_state_est.cpp:12-96           addUpdate roll-forward loop
+//   rbis.cpp:234-266, mav_state_est.cpp:98-189   EKF smoother step and backwards pass
 //   update_history.cpp:5-54           time-ordered multimap history
 // Where the reference uses heap-allocated Eigen::MatrixXd this file uses std::vector<double>; where
 // it uses fixed-size Eigen matrices this file uses fixed arrays.  Matrices are column-major like
