@@ -258,6 +258,20 @@ def smooth_ensemble(vec, quat, cov, utime0, q_params, imu, streams, events, smoo
     return dict(post_vec=pv, post_quat=pq, post_cov=pc)
 
 
+def notch_cascade(x, notch_freq, fs=1000.0, n_stages=3, state=None):
+    """InsHandler::doFilter on one channel (MSE/sensor_handlers.cpp:155-162 over estimate_tools' IIRNotch): n_stages notch
+    filters at notch_freq * 2^i in cascade.  Returns (y, state [n_stages][4] = x0,x1,y0,y1 per stage, coeffs [n_stages][6])."""
+    lib = load()
+    lib.orc_notch_cascade.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orc_notch_cascade.restype = None
+    x = _a(x)
+    y = np.empty_like(x)
+    st = np.zeros((n_stages, 4)) if state is None else _a(state, 4 * n_stages).reshape(n_stages, 4).copy()
+    co = np.zeros((n_stages, 6))
+    lib.orc_notch_cascade(float(notch_freq), float(fs), int(n_stages), x.size, x.ctypes.data, y.ctypes.data, st.ctypes.data, co.ctypes.data)
+    return y, st, co
+
+
 def noise_id_neg_loglik(vec, quat, cov, dt, q_gyro, q_accel, n_window, active=(3, 4, 5, 6, 7, 8, 9, 10, 11)):
     """state-estimator/src/noise_id/noise_id.cpp:9-65 for ONE (q_gyro, q_accel): truth history vec [T1][21],
     quat [T1][4], cov [T1][441] (column-major RBIM per row) -> (negative log-likelihood, per-window errors [W][21])."""

@@ -1,6 +1,7 @@
 // oracle_capi.cpp -- extern "C" face of the CPU ORACLE for ctypes (test infrastructure, NOT product
 // code; PARITY UNPINNED, see rbis_oracle.hpp).  Flat double arrays; matrices column-major.
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -285,6 +286,25 @@ void orc_ekf_smoothing_step(const double* np_vec, const double* np_quat, const d
   ekfSmoothingStep(makeState(np_vec, np_quat), getCov(np_cov), makeState(n_vec, n_quat), getCov(n_cov), dt, cur, P);
   putState(cur, c_vec, c_quat);
   putCov(P, c_cov);
+}
+
+// InsHandler::doFilter (sensor_handlers.cpp:155-162) on ONE channel: n_stages notch filters at notch_freq * 2^i, fs,
+// in cascade over n samples; state (x0,x1,y0,y1 per stage) in/out so that calls can be chained.  coeffs (optional): b,a per stage.
+void orc_notch_cascade(double notch_freq, double fs, int n_stages, int64_t n, const double* in, double* out, double* state,
+                       double* coeffs) {
+  std::vector<IIRNotch> f;
+  for (int i = 0; i < n_stages; i++) {
+    f.emplace_back(notch_freq * std::pow(2, i), fs);
+    if (state) { f[i].x[0] = state[4 * i]; f[i].x[1] = state[4 * i + 1]; f[i].y[0] = state[4 * i + 2]; f[i].y[1] = state[4 * i + 3]; }
+    if (coeffs) for (int k = 0; k < 3; k++) { coeffs[6 * i + k] = f[i].b[k]; coeffs[6 * i + 3 + k] = f[i].a[k]; }
+  }
+  for (int64_t k = 0; k < n; k++) {
+    double v = in[k];
+    for (int i = 0; i < n_stages; i++) v = f[i].processSample(v);
+    out[k] = v;
+  }
+  if (state)
+    for (int i = 0; i < n_stages; i++) { state[4 * i] = f[i].x[0]; state[4 * i + 1] = f[i].x[1]; state[4 * i + 2] = f[i].y[0]; state[4 * i + 3] = f[i].y[1]; }
 }
 
 }  // extern "C"

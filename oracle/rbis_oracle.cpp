@@ -609,6 +609,35 @@ double MavStateEstimator::getMeasurementsLogLikelihood() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// IIR notch: estimate_tools/src/estimate_tools/iir_notch.cpp:3-60
+// ------------------------------------------------------------------------------------------------
+IIRNotch::IIRNotch(double notch_freq, double fs) {
+  const double Wo = notch_freq / (fs / 2);  // :6
+  const double Bw = Wo;
+  secondOrderNotch(Wo, Bw, b, a);
+  x[0] = x[1] = y[0] = y[1] = 0;
+}
+void IIRNotch::secondOrderNotch(double Wo, double BW, double num[3], double den[3]) {
+  const double Ab = std::fabs(10 * std::log10(.5));  // :18
+  BW = BW * M_PI;
+  Wo = Wo * M_PI;
+  const double Gb = std::pow(10, -Ab / 20.);
+  const double beta = (std::sqrt(1.0 - Gb * Gb) / Gb) * std::tan(BW / 2.0);
+  const double gain = 1 / (1 + beta);
+  num[0] = gain * 1.0; num[1] = gain * (-2.0 * std::cos(Wo)); num[2] = gain * 1;  // :30
+  den[0] = 1.0; den[1] = -2 * gain * std::cos(Wo); den[2] = 2 * gain - 1;          // :31
+}
+double IIRNotch::processSample(double input) {
+  // x_temp = (input, x0, x1), y_temp = (0, y0, y1); output = x_temp.b - y_temp.a   (:37-50)
+  const double xb = (input * b[0] + x[0] * b[1]) + x[1] * b[2];
+  const double ya = (0 * a[0] + y[0] * a[1]) + y[1] * a[2];
+  const double output = xb - ya;
+  x[1] = x[0]; x[0] = input;
+  y[1] = y[0]; y[0] = output;
+  return output;
+}
+
+// ------------------------------------------------------------------------------------------------
 // EKF smoother: rbis.cpp:234-266 and mav_state_est.cpp:98-189
 // ------------------------------------------------------------------------------------------------
 void ekfSmoothingStep(const RBIS& next_state_pred, const RBIM& next_cov_pred, const RBIS& next_state, const RBIM& next_cov,

@@ -123,6 +123,17 @@ double loglike_normalized(int n, const double* x, const double* mu, const double
 // negLogLikelihood over the active index set (noise_id.cpp:44-65)
 double negLogLikelihood(const std::vector<RBIS>& state_errors, const std::vector<RBIM>& covs, int n_active, const int32_t* active_inds);
 
+// ---- IMU conditioning ("next" row 4 of SURVEY.md 8f): second-order IIR notch, estimate_tools/src/estimate_tools/
+// iir_notch.cpp:3-60, run as a cascade on the accelerometer channels by InsHandler::doFilter
+// (state-estimator/src/mav_state_est/sensor_handlers.cpp:29-41,155-162) ----
+struct IIRNotch {
+  double b[3], a[3];  // numerator / denominator (iir_notch.cpp:17-33)
+  double x[2], y[2];  // carried inputs / outputs
+  IIRNotch(double notch_freq, double fs);
+  static void secondOrderNotch(double Wo, double BW, double num[3], double den[3]);
+  double processSample(double input);  // iir_notch.cpp:35-60
+};
+
 // ---- update objects: rbis_update_interface.hpp:8-120 ----
 class RBISUpdateInterface {
  public:

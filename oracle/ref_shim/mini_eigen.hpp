@@ -372,6 +372,17 @@ std::ostream& operator<<(std::ostream& os, const MatrixBase<A>& a) {
   return os;
 }
 
+// ---- comma initialiser for vectors: `x << a, b;` (estimate_tools/iir_notch.cpp:11,53) ----
+template <class M>
+struct CommaInitializer {
+  M& m;
+  int k;
+  CommaInitializer(M& m_, double v) : m(m_), k(0) { m.data()[k++] = v; }
+  CommaInitializer& operator,(double v) { m.data()[k++] = v; return *this; }
+};
+template <class T, int R>
+CommaInitializer<Matrix<T, R, 1> > operator<<(Matrix<T, R, 1>& m, double v) { return CommaInitializer<Matrix<T, R, 1> >(m, v); }
+
 // ---- asDiagonal ----
 template <class V>
 class DiagonalWrapper {
