@@ -238,6 +238,17 @@ int rbis_batch_smooth_backward(rbis_batch_t* h, int32_t next_pred_slot, int32_t 
 /* Read a ring slot back: vec [21][N], quat [4][N], cov [441][N], loglik [N]; any may be NULL. */
 int rbis_batch_get_snapshot(rbis_batch_t* h, int32_t slot, double* vec, double* quat, double* cov, double* loglik, int mem);
 
+/* ---- IMU conditioning ("next" row 4 of SURVEY.md 8f): the accelerometer notch cascade of the Atlas INS path,
+ * InsHandler::doFilter (MSE/sensor_handlers.cpp:155-162) over IIRNotch (estimate_tools/src/estimate_tools/
+ * iir_notch.cpp:3-60), for every column of an IMU chunk at once.
+ * configure: n_stages filters at notch_freq * 2^i, i = 0.., sample rate fs (the reference: 3 stages, fs = 1000,
+ * MSE/sensor_handlers.cpp:29-41), for chunks of `cols` columns (N, or the column count of the IMU column map); resets
+ * the carried samples to zero as the IIRNotch constructor does.
+ * filter: filters rows 3..5 (accelerometer x,y,z) of imu [rows][6][cols] IN PLACE, continuing from the state the
+ * previous call left, so a log can be conditioned chunk by chunk before rbis_batch_run_fused consumes it. */
+int rbis_batch_notch_configure(rbis_batch_t* h, double notch_freq, double fs, int n_stages, int64_t cols);
+int rbis_batch_notch_filter(rbis_batch_t* h, double* imu, int64_t rows, int mem);
+
 /* ---- ensemble statistics against a truth state (error definition of
  * SE/noise_id/noise_id.cpp:37-38; NEES over velocity+chi+position as roll_forward.cpp:54-57).
  * truth_vec [21] / truth_quat [4] (host) shared by all filters, or per-filter [21][N] / [4][N] (`mem`)

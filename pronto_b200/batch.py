@@ -152,6 +152,17 @@ class RBISBatch:
         capi.check(self.lib.rbis_batch_smooth_backward(self.h, int(next_pred_slot), int(next_slot), len(steps),
                                                        steps.ctypes.data, float(dt)))
 
+    def notch_configure(self, notch_freq, fs=1000.0, n_stages=3, cols=None):
+        """Accelerometer notch cascade of InsHandler::doFilter (MSE/sensor_handlers.cpp:29-41,155-162)."""
+        self._notch_cols = int(self.N if cols is None else cols)
+        capi.check(self.lib.rbis_batch_notch_configure(self.h, float(notch_freq), float(fs), int(n_stages), self._notch_cols))
+
+    def notch_filter(self, imu):
+        """Filters the accelerometer rows of imu [rows][6][cols] in place (numpy host array or torch CUDA tensor)."""
+        rows = int(imu.shape[0])
+        ptr, mem = _ptr(imu, (rows, 6, self._notch_cols), "imu")
+        capi.check(self.lib.rbis_batch_notch_filter(self.h, ptr, rows, mem))
+
     def set_filter(self, n, vec, quat, cov, loglik=0.0):
         vec = np.ascontiguousarray(vec, dtype=np.float64); quat = np.ascontiguousarray(quat, dtype=np.float64)
         cov = np.ascontiguousarray(cov, dtype=np.float64)

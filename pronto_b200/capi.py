@@ -73,6 +73,8 @@ PROTOTYPES = {
     "rbis_batch_stream": (C.c_void_p, [C.c_void_p]),
     "rbis_batch_launch_count": (C.c_int64, [C.c_void_p]),
     "rbis_batch_last_kernel_variant": (C.c_int, [C.c_void_p]),
+    "rbis_batch_notch_configure": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int64]),
+    "rbis_batch_notch_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "rbis_smooth_plan": (C.c_int64, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rbis_batch_smooth_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_double]),
     "rbis_batch_get_snapshot": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

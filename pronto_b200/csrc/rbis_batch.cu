@@ -111,6 +111,11 @@ struct rbis_batch {
   int decoupled = -1;
   std::vector<char> snap_dc;
   int* d_flag = nullptr;
+  // ---- accelerometer notch cascade (rbis_batch_notch_*) ----
+  rbisk::NotchCoeffs notch{};
+  double* d_notch_state = nullptr;  // [3][MAX_NOTCH][4][notch_cols]
+  int64_t notch_cols = 0;
+  DevBuf notch_stage;               // device copy of a host chunk
   int last_variant = -1;  // kernel variant of the last fused launch: 0 dense, 1 dense + general measurements, 2 decoupled
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
@@ -603,7 +608,8 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   }
   if (h->pre_evt) cudaEventDestroy(h->pre_evt);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
-  cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag);
+  cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag); cudaFree(h->d_notch_state);
+  h->notch_stage.release();
   for (auto& m : h->d_map) cudaFree(m);
   h->full_cov.release(); h->misc.release(); h->stats_async.release();
   for (auto& s : h->slots) {
@@ -1082,6 +1088,63 @@ int rbis_batch_get_snapshot(rbis_batch_t* h, int32_t slot, double* vec, double* 
     if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(cov, dst, N * 441 * sizeof(double), kind, h->stream));
   }
   if (mem == RBIS_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int rbis_batch_notch_configure(rbis_batch_t* h, double notch_freq, double fs, int n_stages, int64_t cols) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (n_stages < 1 || n_stages > rbisk::MAX_NOTCH) return fail(RBIS_ERR_INVALID, "n_stages must be in [1, %d]", rbisk::MAX_NOTCH);
+  if (!(notch_freq > 0) || !(fs > 0) || cols <= 0) return fail(RBIS_ERR_INVALID, "notch_freq, fs and cols must be positive");
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_stages; i++) {
+    // IIRNotch::IIRNotch + secondOrderNotch, estimate_tools/src/estimate_tools/iir_notch.cpp:3-33, with the stage
+    // frequencies of InsHandler (MSE/sensor_handlers.cpp:33-41: notch_freq * 2^i)
+    double Wo = (notch_freq * std::pow(2, i)) / (fs / 2);
+    double BW = Wo;
+    const double Ab = std::fabs(10 * std::log10(.5));
+    BW = BW * M_PI;
+    Wo = Wo * M_PI;
+    const double Gb = std::pow(10, -Ab / 20.);
+    const double beta = (std::sqrt(1.0 - Gb * Gb) / Gb) * std::tan(BW / 2.0);
+    const double gain = 1 / (1 + beta);
+    h->notch.b[i][0] = gain * 1.0; h->notch.b[i][1] = gain * (-2.0 * std::cos(Wo)); h->notch.b[i][2] = gain * 1;
+    h->notch.a[i][0] = 1.0; h->notch.a[i][1] = -2 * gain * std::cos(Wo); h->notch.a[i][2] = 2 * gain - 1;
+  }
+  h->notch.n_stages = n_stages;
+  cudaFree(h->d_notch_state);
+  h->d_notch_state = nullptr;
+  const size_t n = (size_t)3 * rbisk::MAX_NOTCH * 4 * (size_t)cols;
+  CUDA_TRY(cudaMalloc(&h->d_notch_state, n * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(h->d_notch_state, 0, n * sizeof(double), h->stream));  // x = y = 0, iir_notch.cpp:10-13
+  h->notch_cols = cols;
+  return 0;
+}
+
+int rbis_batch_notch_filter(rbis_batch_t* h, double* imu, int64_t rows, int mem) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!h->d_notch_state) return fail(RBIS_ERR_STATE, "rbis_batch_notch_configure has not been called");
+  if (!imu || rows < 0) return fail(RBIS_ERR_INVALID, "bad imu chunk");
+  if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (rows == 0) return 0;
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  const size_t count = (size_t)rows * 6 * (size_t)h->notch_cols;
+  double* d = imu;
+  if (mem == RBIS_MEM_HOST) {
+    if (h->notch_stage.ensure(count)) return fail(RBIS_ERR_ALLOC, "staging allocation failed");
+    d = h->notch_stage.p;
+    CUDA_TRY(cudaMemcpyAsync(d, imu, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  rbisk::notch_kernel<<<(unsigned)((h->notch_cols + 127) / 128), 128, 0, h->stream>>>(d, (long long)rows, (long long)h->notch_cols,
+                                                                                     h->d_notch_state, h->notch);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  if (mem == RBIS_MEM_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(imu, d, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 
