@@ -150,6 +150,28 @@ def test_gpu_backward_pass_matches_oracle(oracle, trailing, N):
 
 
 @pytest.mark.gpu
+def test_gpu_backward_pass_is_reproducible():
+    """Warp-level shared-memory hand-offs in rbis_smooth_kernel: two runs from the same forward pass give the same bits
+    (compute-sanitizer's racecheck is not available on the GPU pool)."""
+    N, T = 300, 80
+    sc = scenario(N, T)
+    st = sc["st"]
+    ev = list(st["events"])
+    ops, is_ins, slot = smoother.forward_program(ev)
+    outs = []
+    with RBISBatch(N, snapshot_slots=len(is_ins)) as b:
+        b.set_process_noise(*nominal_q())
+        for rep in range(3):
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            b.run_fused(ops, imu=st["imu"], streams=gpu_streams(st))
+            alias = smoother.smooth(b, is_ins, slot, 1e-3)
+            outs.append(b.get_snapshot(int(alias[1])))
+    for o in outs[1:]:
+        for x, y in zip(o, outs[0]):
+            assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
 def test_gpu_smoother_errors():
     with RBISBatch(8, snapshot_slots=3) as b:
         steps = np.zeros(1, dtype=smoother.STEP_DTYPE)
