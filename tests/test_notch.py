@@ -40,6 +40,37 @@ def test_oracle_cascade_vs_scipy_and_reference(oracle):
     assert np.max(np.abs(y - ry)) < 1e-12 and np.max(np.abs(st - rst)) < 1e-12
 
 
+def _ref_next():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "rbis_reference_golden_next.npz"))
+
+
+def _golden_signal(n=3000, seed=11):  # as tests/golden/make_reference_golden_next.py:notch_signal
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 1000.0
+    return rng.normal(size=n) * 0.3 + 2.0 * np.sin(2 * np.pi * 85 * t) + 9.8
+
+
+def test_oracle_cascade_matches_reference_golden(oracle):
+    g = _ref_next()
+    y, st, co = oracle.notch_cascade(_golden_signal(), 85.0, 1000.0, 3)
+    assert np.array_equal(co, g["notch_coeffs"])
+    assert np.max(np.abs(y - g["notch_y"])) < 1e-12 and np.max(np.abs(st - g["notch_state"])) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_notch_matches_reference_golden():
+    g = _ref_next()
+    x = _golden_signal()
+    imu = np.zeros((len(x), 6, 5))
+    imu[:, 3:6, :] = x[:, None, None]
+    with RBISBatch(5) as b:
+        b.notch_configure(85.0, 1000.0, 3)
+        b.notch_filter(imu)
+    assert np.max(np.abs(imu[:, 3:6, :] - g["notch_y"][:, None, None])) < 1e-12 and np.all(imu[:, :3] == 0)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("device_resident", [False, True])
 def test_gpu_notch_matches_oracle_chunk_by_chunk(oracle, device_resident):

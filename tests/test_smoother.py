@@ -119,6 +119,53 @@ def test_plan_rejects_a_history_without_imu_steps(rbis_lib):
         smoother.plan(np.zeros(4, dtype=np.uint8), np.arange(4, dtype=np.int32))
 
 
+@pytest.fixture(scope="module")
+def ref_next():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "rbis_reference_golden_next.npz"))
+
+
+def _golden_case(trailing):
+    sys_path = os.path.join(os.path.dirname(__file__), "golden")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_reference_golden_next", os.path.join(sys_path, "make_reference_golden_next.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.smoothing_events(trailing)
+
+
+@pytest.mark.parametrize("name,trailing", [("plain", False), ("trailing", True)])
+def test_oracle_backwards_pass_matches_reference_golden(oracle, ref_next, name, trailing):
+    """Fixture made by the reference's own compiled sources (tests/golden/make_reference_golden_next.py)."""
+    sc, ev = _golden_case(trailing)
+    st = sc["st"]
+    a = oracle.smooth_ensemble(sc["vec"], sc["quat"], sc["cov"], 0, nominal_q(), st["imu"], oracle_streams(st), ev, 1e-3)
+    for k in ("vec", "quat", "cov"):
+        assert np.max(np.abs(a[f"post_{k}"] - ref_next[f"smooth_{name}_{k}"])) < 1e-12, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,trailing", [("plain", False), ("trailing", True)])
+def test_gpu_backward_pass_matches_reference_golden(ref_next, name, trailing):
+    sc, ev = _golden_case(trailing)
+    st = sc["st"]
+    N = sc["vec"].shape[1]
+    ops, is_ins, slot = smoother.forward_program(ev)
+    with RBISBatch(N, snapshot_slots=len(is_ins)) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(ops, imu=st["imu"], streams=gpu_streams(st))
+        alias = smoother.smooth(b, is_ins, slot, 1e-3)
+        for u in range(1, len(is_ins)):
+            gv, gq, gP, _ = b.get_snapshot(int(alias[u]))
+            rv, rq, rP = (ref_next[f"smooth_{name}_{k}"][u - 1] for k in ("vec", "quat", "cov"))
+            assert np.max(np.abs(gv - rv) / np.maximum(1.0, np.abs(rv))) < 1e-9, u
+            assert np.max(np.abs(gq - rq)) < 1e-9, u
+            d = np.sqrt(np.abs(rP.reshape(21, 21, N)[np.arange(21), np.arange(21)]))
+            scale = np.maximum(d[:, None, :] * d[None, :, :], 1e-30).reshape(441, N)
+            assert np.max(np.abs(gP - rP) / scale) < 1e-7, u
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("trailing,N", [(False, 37), (True, 130)])
 def test_gpu_backward_pass_matches_oracle(oracle, trailing, N):
