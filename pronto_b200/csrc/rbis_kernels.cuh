@@ -63,6 +63,9 @@
 #ifndef RBIS_PARK_STATE
 #define RBIS_PARK_STATE 0
 #endif
+#ifndef RBIS_STAGGER_NS
+#define RBIS_STAGGER_NS 0
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -1174,6 +1177,11 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
     return o;
   };
   const long long imu_n = p.imu_map ? (long long)__ldg(p.imu_map + n) : n;
+#if RBIS_STAGGER_NS
+  // the warps of a scheduler run the same program from the same start, so their FP64-dense and latency-bound phases
+  // coincide; a one-time skew between the warp quartets spreads them over the step
+  if (warp >> 2) __nanosleep((unsigned)(warp >> 2) * RBIS_STAGGER_NS);
+#endif
   Op op_next = load_op(0);
   for (long long oi = 0; oi < p.n_ops; oi++) {
     const Op op = op_next;
