@@ -593,6 +593,69 @@ def run_b200(args):
         for w in (-1, 0, 1):
             b.set_column_map(w, None)
 
+    # ---- informational: the "next" rows of SURVEY.md 8f on this GPU (rank 0, N=1 only) ----
+    next_rows = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        from pronto_b200 import smoother
+
+        next_rows = {}
+        # accelerometer notch cascade (HBM-bound): one 200-row chunk of all N columns filtered in place, 10 calls
+        hbm_peak, hbm_src = 6544.7, "fallback: copy bandwidth of this pool's MEASURED_PEAKS.json at the time of writing"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        buf = chunks[0]["imu"].clone()
+        b.notch_configure(85.0, 1000.0, 3)
+        b.notch_filter(buf)
+        b.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for _ in range(10):
+            b.notch_filter(buf)
+        n1.record(stream)
+        b.synchronize()
+        torch.cuda.synchronize()
+        n_ms = n0.elapsed_time(n1) / 10
+        n_bytes = Tc * 3 * N * 8 * 2
+        next_rows["notch_cascade"] = {"kernel": "notch_kernel", "ms_per_call": n_ms, "rows": Tc, "columns": N,
+                                      "roofline": {"bound": "hbm", "achieved": n_bytes / (n_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                   "frac": n_bytes / (n_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                                                   "algorithmic_bytes": "24 B read + 24 B written per row and column (3 accelerometer channels)"},
+                                      "value": Tc * N / (n_ms * 1e-3), "unit": "column-samples/s"}
+        del buf
+        # EKF smoother: forward pass that snapshots every update, then the backward pass
+        Ns, Ts = min(4096, N), 100
+        ev_s, _, _ = chunk_events(Ts, 0)
+        ops_s, is_ins, slot = smoother.forward_program(ev_s)
+        sub = lambda t, rows: t[:rows, ..., :Ns].contiguous()
+        ch = chunks[0]
+        n_lego_s, n_pose_s = sum(1 for e in ev_s if e[0] == 1 and e[1] == 0), sum(1 for e in ev_s if e[0] == 1 and e[1] == 1)
+        with RBISBatch(Ns, device=local, snapshot_slots=len(is_ins)) as bs:
+            bs.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
+            st_s = [MeasStream(synth.LEGODO_IDX, sub(ch["legodo"], n_lego_s), R_lego),
+                    MeasStream(synth.POSE_IDX, sub(ch["pose_z"], n_pose_s), R_pose, quat=sub(ch["pose_q"], n_pose_s))]
+            imu_s = sub(ch["imu"], Ts)
+            np_slot, n_slot, steps_s, alias = smoother.plan(is_ins, slot)
+            best_f, best_b = 1e30, 1e30
+            for rep in range(2):
+                bs.set_state(vec0[:, :Ns].contiguous(), quat0[:, :Ns].contiguous(), cov0[:, :Ns].contiguous())
+                bs.synchronize()
+                t0 = time.perf_counter()
+                bs.run_fused(ops_s, imu=imu_s, streams=st_s)
+                bs.synchronize()
+                t1 = time.perf_counter()
+                bs.smooth_backward(np_slot, n_slot, steps_s, 1e-3)
+                bs.synchronize()
+                t2 = time.perf_counter()
+                best_f, best_b = min(best_f, t1 - t0), min(best_b, t2 - t1)
+        next_rows["ekf_smoother"] = {"kernel": "rbis_smooth_kernel", "filters": Ns, "smoothing_steps": int(len(steps_s)),
+                                     "backward_ms": best_b * 1e3, "value": Ns * len(steps_s) / best_b, "unit": "smoothing steps/s",
+                                     "forward_with_snapshots_ms": best_f * 1e3, "timing": "host wall clock around synchronised calls"}
+        log(f"[rank 0] next rows: notch {next_rows['notch_cascade']['roofline']['achieved']:.0f} GB/s "
+            f"({100 * next_rows['notch_cascade']['roofline']['frac']:.0f} % of {hbm_peak:.0f}), smoother {next_rows['ekf_smoother']['value'] / 1e6:.1f} M steps/s")
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -638,7 +701,7 @@ def run_b200(args):
                          "hbm_stream_gbs": in_bytes / (k_ms * 1e-3) / 1e9,
                          **hw,
                          "note": "achieved/frac count the dense ALGORITHMIC flops of SURVEY.md 8d (task contract); the kernel exploits the block structure of Ad and the symmetry of P and executes ~11x fewer, so frac exceeds 1. achieved_hw/frac_hw count executed flops; fp64_pipe_busy_frac = executed FP64 warp-instructions x 2 issue cycles / (SM sub-partition cycles), cf. ncu sm__pipe_fp64_cycles_active in profiles/"},
-            "cpu_baseline": cpu, "e2e": e2e, "sweep_shared_inputs": sweep, "dense_variant": dense_leg, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "sweep_shared_inputs": sweep, "dense_variant": dense_leg, "next_rows": next_rows, "gpu_launches": launches, "clocks": clocks,
             "ensemble": {"mean_nees9": summ["mean_nees"], "nees_in_95pct": summ["nees_in_95pct"], "non_finite": summ["non_finite"]},
         }
         emit(line)

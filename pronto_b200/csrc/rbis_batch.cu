@@ -1137,8 +1137,8 @@ int rbis_batch_notch_filter(rbis_batch_t* h, double* imu, int64_t rows, int mem)
     d = h->notch_stage.p;
     CUDA_TRY(cudaMemcpyAsync(d, imu, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
-  rbisk::notch_kernel<<<(unsigned)((h->notch_cols + 127) / 128), 128, 0, h->stream>>>(d, (long long)rows, (long long)h->notch_cols,
-                                                                                     h->d_notch_state, h->notch);
+  rbisk::notch_kernel<<<dim3((unsigned)((h->notch_cols + 127) / 128), 3), 128, 0, h->stream>>>(d, (long long)rows, (long long)h->notch_cols,
+                                                                                              h->d_notch_state, h->notch);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   if (mem == RBIS_MEM_HOST) {

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
 // ------------------------------------------------------------------------------------------------
 // IMU conditioning ("next" row 4 of SURVEY.md 8f): InsHandler::doFilter (MSE/sensor_handlers.cpp:155-162) = a cascade of
 // IIRNotch::processSample (estimate_tools/src/estimate_tools/iir_notch.cpp:35-60) on the three accelerometer channels,
-// for every column of an IMU chunk [rows][6][cols], in place.  One thread per column; the 3 channels x n_stages x
+// for every column of an IMU chunk [rows][6][cols], in place.  One thread per column and channel; its n_stages x
 // (x0,x1,y0,y1) of filter state stay in registers over the rows of the chunk and persist in `state`
 // ([3][MAX_NOTCH][4][cols]) between calls.  HBM-bound: 24 B read + 24 B written per row and column.
 // ------------------------------------------------------------------------------------------------
@@ -198,42 +198,48 @@ struct NotchCoeffs {
 };
 __global__ void __launch_bounds__(128) notch_kernel(double* __restrict__ imu, long long rows, long long cols, double* __restrict__ state,
                                                     const __grid_constant__ NotchCoeffs co) {
+  // one thread per (column, accelerometer channel): blockIdx.y is the channel
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.y;
   if (c >= cols) return;
-  double st[3][MAX_NOTCH][4];
+  double st[MAX_NOTCH][4];
 #pragma unroll
-  for (int ch = 0; ch < 3; ch++)
+  for (int i = 0; i < MAX_NOTCH; i++)
 #pragma unroll
-    for (int i = 0; i < MAX_NOTCH; i++)
+    for (int k = 0; k < 4; k++) st[i][k] = (i < co.n_stages) ? state[((long long)(ch * MAX_NOTCH + i) * 4 + k) * cols + c] : 0.0;
+  auto sample = [&](double v) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) st[ch][i][k] = (i < co.n_stages) ? state[((long long)(ch * MAX_NOTCH + i) * 4 + k) * cols + c] : 0.0;
-  for (long long r = 0; r < rows; r++) {
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-      double* p = imu + (r * 6 + 3 + ch) * cols + c;
-      double v = *p;
-#pragma unroll
-      for (int i = 0; i < MAX_NOTCH; i++) {
-        if (i < co.n_stages) {
-          // output = (input, x0, x1) . b - (0, y0, y1) . a, summed left to right as Eigen's 3-vector dot does
-          const double xb = v * co.b[i][0] + st[ch][i][0] * co.b[i][1] + st[ch][i][1] * co.b[i][2];
-          const double ya = 0 * co.a[i][0] + st[ch][i][2] * co.a[i][1] + st[ch][i][3] * co.a[i][2];
-          const double out = xb - ya;
-          st[ch][i][1] = st[ch][i][0]; st[ch][i][0] = v;
-          st[ch][i][3] = st[ch][i][2]; st[ch][i][2] = out;
-          v = out;
-        }
+    for (int i = 0; i < MAX_NOTCH; i++) {
+      if (i < co.n_stages) {
+        // output = (input, x0, x1) . b - (0, y0, y1) . a, summed left to right as Eigen's 3-vector dot does
+        const double xb = v * co.b[i][0] + st[i][0] * co.b[i][1] + st[i][1] * co.b[i][2];
+        const double ya = 0 * co.a[i][0] + st[i][2] * co.a[i][1] + st[i][3] * co.a[i][2];
+        const double out = xb - ya;
+        st[i][1] = st[i][0]; st[i][0] = v;
+        st[i][3] = st[i][2]; st[i][2] = out;
+        v = out;
       }
-      *p = v;
     }
+    return v;
+  };
+  // the recursion is serial in time, the loads are not: NOTCH_ROWS rows are fetched ahead of the arithmetic
+  constexpr int NOTCH_ROWS = 8;
+  double* base = imu + (long long)(3 + ch) * cols + c;
+  const long long stride = 6 * cols;
+  long long r = 0;
+  for (; r + NOTCH_ROWS <= rows; r += NOTCH_ROWS) {
+    double v[NOTCH_ROWS];
+#pragma unroll
+    for (int k = 0; k < NOTCH_ROWS; k++) v[k] = base[(r + k) * stride];
+#pragma unroll
+    for (int k = 0; k < NOTCH_ROWS; k++) base[(r + k) * stride] = sample(v[k]);
   }
+  for (; r < rows; r++) base[r * stride] = sample(base[r * stride]);
 #pragma unroll
-  for (int ch = 0; ch < 3; ch++)
+  for (int i = 0; i < MAX_NOTCH; i++)
 #pragma unroll
-    for (int i = 0; i < MAX_NOTCH; i++)
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (i < co.n_stages) state[((long long)(ch * MAX_NOTCH + i) * 4 + k) * cols + c] = st[ch][i][k];
+    for (int k = 0; k < 4; k++)
+      if (i < co.n_stages) state[((long long)(ch * MAX_NOTCH + i) * 4 + k) * cols + c] = st[i][k];
 }
 
 }  // namespace rbisk
