@@ -63,6 +63,9 @@
 #ifndef RBIS_PARK_STATE
 #define RBIS_PARK_STATE 0
 #endif
+#ifndef RBIS_SM_PAIR
+#define RBIS_SM_PAIR 0  // 1: shared slots 2k, 2k+1 of a lane are adjacent (16-byte pairs), so that loads of consecutive rows merge
+#endif
 #ifndef RBIS_STAGGER_NS
 #define RBIS_STAGGER_NS 0
 #endif
@@ -116,7 +119,7 @@ __host__ __device__ constexpr bool slot_in_tm(int i, int j) {
 #if RBIS_PLACEMENT == 0
   return is_act(i) && is_act(j);
 #elif RBIS_PLACEMENT == 2
-  return (i >= 9 && !(i >= 12 && i < 15)) && (j >= 9 && !(j >= 12 && j < 15));
+  return ((i >= 9 && !(i >= 12 && i < 15)) && (j >= 9 && !(j >= 12 && j < 15))) || (RBIS_SM_PAIR && i == 5 && j == 20);
 #else
   return !(is_act(i) && is_act(j)) || i >= 18 || (i == 17 && j == 17);
 #endif
@@ -154,8 +157,17 @@ constexpr int N_SM = kPlace.n_sm;   // slots in shared memory
 constexpr int TM_COLS = (512 / ((TPB + 127) / 128)) & ~1;
 static_assert(TPB % 32 == 0, "whole warps");
 static_assert(2 * (N_TM + RBIS_PARK_STATE_SLOTS) <= TM_COLS, "tensor-memory share of a thread exceeded");
-static_assert(N_SM * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
-constexpr int SMEM_BYTES = N_SM * TPB * 8;
+constexpr int N_SM_ALLOC = RBIS_SM_PAIR ? ((N_SM + 1) & ~1) : N_SM;
+static_assert(N_SM_ALLOC * TPB * 8 + 64 <= 232448, "shared-memory part exceeds 227 KB per CTA");
+constexpr int SMEM_BYTES = N_SM_ALLOC * TPB * 8;
+// offset (in doubles, from the lane's base pointer) of shared slot k
+__host__ __device__ constexpr int sm_off(int k) {
+#if RBIS_SM_PAIR
+  return (k >> 1) * 2 * TPB + (k & 1);
+#else
+  return k * TPB;
+#endif
+}
 
 // ---- decoupled filters (DC kernels) ---------------------------------------------------------------
 // The rows of Ad for omega (0..2) and a (12..14) are identity and its columns for them are zero, so the couplings
@@ -369,7 +381,7 @@ struct Cov {
   __device__ __forceinline__ void set(double v) {
     constexpr int i = I < J ? I : J, j = I < J ? J : I;
     if constexpr (in_tm(i, j)) tm_st2(tm + 2 * tm_index(i, j), v);
-    else Ps[sm_index(i, j) * TPB] = v;
+    else Ps[sm_off(sm_index(i, j))] = v;
   }
   template <int R0, int C>
   __device__ __forceinline__ void setcol3(const V3& v) {
@@ -385,13 +397,13 @@ struct Cov {
       tm_wait_ld();
       return tm_settle(lo, hi);
     }
-    return Ps[k * TPB];
+    return Ps[sm_off(k)];
   }
   __device__ __forceinline__ void setr(int i, int j, double v) {
     const int s_ = slot(i, j);
     const int k = c_place.idx[s_];
     if (c_place.tm[s_]) { tm_st2(tm + 2 * k, v); tm_wait_st(); }
-    else Ps[k * TPB] = v;
+    else Ps[sm_off(k)] = v;
   }
 };
 
@@ -411,7 +423,7 @@ __device__ __forceinline__ void issue(const Cov& P, Buf<L::N>& b) {
 #else
     if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), b.lo[k], b.hi[k]);
 #endif
-    else b.d[k] = P.Ps[sm_index(i, j) * TPB];
+    else b.d[k] = P.Ps[sm_off(sm_index(i, j))];
   });
 }
 template <class L>
@@ -921,7 +933,7 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
 #else
           if constexpr (in_tm(i, j)) tm_ld2(P.tm + 2 * tm_index(i, j), nxt.lo[k], nxt.hi[k]);
 #endif
-          else nxt.d[k] = P.Ps[sm_index(i, j) * TPB];
+          else nxt.d[k] = P.Ps[sm_off(sm_index(i, j))];
         });
       }
       static_for<len>([&](auto kc) {
@@ -1133,7 +1145,7 @@ __global__ void __maxnreg__(RBIS_MAXNREG) rbis_fused_kernel(const __grid_constan
 __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constant__ KParams p) {
 #endif
   static_assert(!(GENERAL && DC), "the DC variant has no general measurement path");
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ uint32_t tm_base_s;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -1153,7 +1165,7 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   if (!active) n = N - 1;  // idle lanes shadow the last filter and never store
 
   Cov P;
-  P.Ps = smem + tid;
+  P.Ps = smem + (RBIS_SM_PAIR ? 2 * tid : tid);
   P.tm = tm_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_COLS);
   FilterState s;
   static_for<NS>([&](auto i) { s.x[i] = p.vec[(long long)i * N + n]; });
