@@ -66,6 +66,21 @@
 #ifndef RBIS_SM_PAIR
 #define RBIS_SM_PAIR 0  // 1: shared slots 2k, 2k+1 of a lane are adjacent (16-byte pairs), so that loads of consecutive rows merge
 #endif
+// The filter-state arithmetic between the covariance sweeps is a serial stretch in which the FP64 pipe idles for all
+// warps of a scheduler at once (they run in step), so its instruction count matters more than its share suggests:
+// RBIS_FAST_SERIAL 1: one reciprocal instead of three divisions in the axis of a rotation increment, squared-norm test
+//                     before chiToQuat;  2: also R computed once per step for R dt, q^-1 g_vec and q v, sin / cos of the
+//                     (small) half angle by their series, |chi| and 1/|chi| from one rsqrt.  Each differs from the
+//                     reference's operation order by a few ulp per step (parity tests: <= 1e-12 per step).
+// RBIS_ONE_LOG 1:     log of the determinant, as the reference writes it (rbis.cpp:142), instead of the sum of the
+//                     logs of the three pivots.
+// Measured (dev/kbench, 113,664 filters): 5.93 -> 6.10 (ONE_LOG) -> 6.44 (FAST_SERIAL 1) -> 6.78 G filter-steps/s (2).
+#ifndef RBIS_FAST_SERIAL
+#define RBIS_FAST_SERIAL 2
+#endif
+#ifndef RBIS_ONE_LOG
+#define RBIS_ONE_LOG 1
+#endif
 #ifndef RBIS_STAGGER_NS
 #define RBIS_STAGGER_NS 0
 #endif
@@ -301,11 +316,50 @@ __device__ __forceinline__ V3 qrot(const Q4& q, const V3& v) {
   V3 c = cross(u, uv);
   return {fma(q.w, uv.x, v.x) + c.x, fma(q.w, uv.y, v.y) + c.y, fma(q.w, uv.z, v.z) + c.z};
 }
+// sin / cos of a small angle by their Taylor series (|x| <= 0.25: truncation below 3e-18 relative), the library routine
+// otherwise: half rotation increments of a 1 kHz filter are ~1e-4
+__device__ __forceinline__ void sincos_small(double x, double* sp, double* cp) {
+#if RBIS_FAST_SERIAL >= 2
+  if (fabs(x) <= 0.25) {
+    const double x2 = x * x;
+    double ps = fma(x2, -1.0 / 6227020800.0, 1.0 / 39916800.0);
+    ps = fma(x2, ps, -1.0 / 362880.0);
+    ps = fma(x2, ps, 1.0 / 5040.0);
+    ps = fma(x2, ps, -1.0 / 120.0);
+    ps = fma(x2, ps, 1.0 / 6.0);
+    *sp = fma(-x * x2, ps, x);
+    double pc = fma(x2, 1.0 / 479001600.0, -1.0 / 3628800.0);
+    pc = fma(x2, pc, 1.0 / 40320.0);
+    pc = fma(x2, pc, -1.0 / 720.0);
+    pc = fma(x2, pc, 1.0 / 24.0);
+    pc = fma(x2, pc, -0.5);
+    *cp = fma(x2, pc, 1.0);
+    return;
+  }
+#endif
+  sincos(x, sp, cp);
+}
 // quaternion of AngleAxis(|chi|, chi/|chi|)
 __device__ __forceinline__ Q4 qexp(const V3& chi, double n) {
   double s, c;
-  sincos(0.5 * n, &s, &c);
+  sincos_small(0.5 * n, &s, &c);
+#if RBIS_FAST_SERIAL
+  const double rn = 1.0 / n;  // one reciprocal instead of three divisions (<= 1 ulp apart per component)
+  return {c, s * (chi.x * rn), s * (chi.y * rn), s * (chi.z * rn)};
+#else
   return {c, s * (chi.x / n), s * (chi.y / n), s * (chi.z / n)};
+#endif
+}
+// the same from the SQUARED norm: one reciprocal square root gives both |chi| and 1/|chi|
+__device__ __forceinline__ Q4 qexp2(const V3& chi, double n2) {
+#if RBIS_FAST_SERIAL >= 2
+  const double rn = rsqrt(n2);
+  double s, c;
+  sincos_small(0.5 * (n2 * rn), &s, &c);
+  return {c, s * (chi.x * rn), s * (chi.y * rn), s * (chi.z * rn)};
+#else
+  return qexp(chi, sqrt(n2));
+#endif
 }
 // subtractQuats(q1, q2) = axis*angle of q2^-1 * q1 (Eigen >= 3.3 AngleAxis, bot_mod2pi)
 __device__ __forceinline__ V3 subtract_quats(const Q4& q1, const Q4& q2) {
@@ -721,9 +775,16 @@ __device__ __forceinline__ void cov_propagate(Cov& P, const Lin& L, AfterPassive
 // chiToQuat on the filter state: fold vec chi into the quaternion when its norm exceeds the tolerance
 __device__ __forceinline__ void fold_chi(FilterState& s, double chi_tol) {
   const V3 c{s.x[6], s.x[7], s.x[8]};
+#if RBIS_FAST_SERIAL
+  // the common case is chi == 0 (folded by the previous update): compare squared norms, root only when folding
+  const double n2 = sumsq3(c.x, c.y, c.z);
+  if (n2 > chi_tol * chi_tol) {
+    const Q4 q = qmul({s.qw, s.qx, s.qy, s.qz}, qexp2(c, n2));
+#else
   const double n = sqrt(sumsq3(c.x, c.y, c.z));
   if (n > chi_tol) {
     const Q4 q = qmul({s.qw, s.qx, s.qy, s.qz}, qexp(c, n));
+#endif
     s.qw = q.w; s.qx = q.x; s.qy = q.y; s.qz = q.z;
     s.x[6] = 0; s.x[7] = 0; s.x[8] = 0;
   }
@@ -746,6 +807,8 @@ __device__ __forceinline__ void add_state_tail(FilterState& s, const V3& dchi, b
 }
 
 // insUpdateState, rbis.cpp:37-75.  gb = q^-1 g_vec at the prior quaternion.
+// P_DONE: the caller has already added dp = (q v) dt to the position (from the prior q and v, as here)
+template <bool P_DONE = false>
 __device__ __forceinline__ void state_propagate(FilterState& s, const V3& gyro, const V3& acc, double dt, const V3& gb,
                                                 double chi_tol, int renorm) {
   const V3 w{gyro.x - s.x[15], gyro.y - s.x[16], gyro.z - s.x[17]};
@@ -756,16 +819,25 @@ __device__ __forceinline__ void state_propagate(FilterState& s, const V3& gyro, 
   const V3 wxv = cross(w, v);
   const V3 dv{(-wxv.x + (gb.x + a.x)) * dt, (-wxv.y + (gb.y + a.y)) * dt, (-wxv.z + (gb.z + a.z)) * dt};
   V3 dchi{w.x * dt, w.y * dt, w.z * dt};
-  const V3 rv = qrot({s.qw, s.qx, s.qy, s.qz}, v);
-  const V3 dp{rv.x * dt, rv.y * dt, rv.z * dt};
+  V3 dp{0, 0, 0};
+  if constexpr (!P_DONE) {
+    const V3 rv = qrot({s.qw, s.qx, s.qy, s.qz}, v);
+    dp = {rv.x * dt, rv.y * dt, rv.z * dt};
+  }
   // dstate.chiToQuat()
-  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   Q4 dq{1, 0, 0, 0};
+#if RBIS_FAST_SERIAL >= 2
+  const double n2 = sumsq3(dchi.x, dchi.y, dchi.z);
+  const bool folded = n2 > chi_tol * chi_tol;
+  if (folded) dq = qexp2(dchi, n2);
+#else
+  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   const bool folded = n > chi_tol;
   if (folded) dq = qexp(dchi, n);
+#endif
   // addState
   s.x[3] += dv.x; s.x[4] += dv.y; s.x[5] += dv.z;
-  s.x[9] += dp.x; s.x[10] += dp.y; s.x[11] += dp.z;
+  if constexpr (!P_DONE) { s.x[9] += dp.x; s.x[10] += dp.y; s.x[11] += dp.z; }
   add_state_tail(s, dchi, folded, dq, chi_tol, renorm);
 }
 
@@ -889,7 +961,14 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   const double d1 = fma(-l10 * l10, d0, S11), r1 = 1.0 / d1;
   const double l21 = fma(-l20 * l10, d0, S21) * r1;
   const double d2 = fma(-l21 * l21, d1, fma(-l20 * l20, d0, S22)), r2 = 1.0 / d2;
+#if RBIS_ONE_LOG
+  // the reference takes ONE logarithm, of the determinant (rbis.cpp:142); the sum of three is the fallback where the
+  // product of the pivots leaves the normal range
+  const double pd = d0 * d1 * d2;
+  const double logdet = (pd > 1e-290 && pd < 1e290) ? log(pd) : log(d0) + log(d1) + log(d2);
+#else
   const double logdet = log(d0) + log(d1) + log(d2);
+#endif
   // Y = L^-1 HP
 #pragma unroll
   for (int c = 0; c < NC; c++) {
@@ -1071,10 +1150,16 @@ __device__ __forceinline__ void meas_finish(FilterState& s, const V3& chi0, doub
                                             int renorm) {
   V3 dchi{s.x[6] - chi0.x, s.x[7] - chi0.y, s.x[8] - chi0.z};
   s.x[6] = chi0.x; s.x[7] = chi0.y; s.x[8] = chi0.z;
-  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   Q4 dq{1, 0, 0, 0};
+#if RBIS_FAST_SERIAL >= 2
+  const double n2 = sumsq3(dchi.x, dchi.y, dchi.z);
+  const bool folded = ctor_folds_chi && (n2 > chi_tol * chi_tol);
+  if (folded) dq = qexp2(dchi, n2);
+#else
+  const double n = sqrt(sumsq3(dchi.x, dchi.y, dchi.z));
   const bool folded = ctor_folds_chi && (n > chi_tol);
   if (folded) dq = qexp(dchi, n);
+#endif
   add_state_tail(s, dchi, folded, dq, chi_tol, renorm);
 }
 
@@ -1221,13 +1306,37 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
 #endif
       const double dt = op.dt;
       const Q4 q{s.qw, s.qx, s.qy, s.qz};
+#if RBIS_FAST_SERIAL >= 2
+      // the rotation matrix is needed for R dt anyway: q^-1 g_vec = -g_val * (third row of R) and q v = R v come from it
+      // (equal to the quaternion forms up to rounding and to |q|^2 - 1, which the reference lets drift at 1e-16 per step)
+      const double tx_ = 2 * q.x, ty_ = 2 * q.y, tz_ = 2 * q.z;
+      const double twx_ = tx_ * q.w, twy_ = ty_ * q.w, twz_ = tz_ * q.w;
+      const double txx_ = tx_ * q.x, txy_ = ty_ * q.x, txz_ = tz_ * q.x;
+      const double tyy_ = ty_ * q.y, tyz_ = tz_ * q.y, tzz_ = tz_ * q.z;
+      const double R00 = 1 - (tyy_ + tzz_), R01 = txy_ - twz_, R02 = txz_ + twy_;
+      const double R10 = txy_ + twz_, R11 = 1 - (txx_ + tzz_), R12 = tyz_ - twx_;
+      const double R20 = txz_ - twy_, R21 = tyz_ + twx_, R22 = 1 - (txx_ + tyy_);
+      const V3 gb{-p.g_val * R20, -p.g_val * R21, -p.g_val * R22};
+      {
+        const double vx = s.x[3], vy = s.x[4], vz = s.x[5];
+        s.x[9] += fma(R02, vz, fma(R01, vy, R00 * vx)) * dt;
+        s.x[10] += fma(R12, vz, fma(R11, vy, R10 * vx)) * dt;
+        s.x[11] += fma(R22, vz, fma(R21, vy, R20 * vx)) * dt;
+      }
+#else
       const V3 gb = qrot(qinv(q), V3{0.0, 0.0, -p.g_val});
+#endif
       Lin L;
       L.v = {s.x[3], s.x[4], s.x[5]};
       L.wd = {s.x[0] * dt, s.x[1] * dt, s.x[2] * dt};  // omega of the PRIOR state (previous sample)
       L.vd = {L.v.x * dt, L.v.y * dt, L.v.z * dt};
       L.gd = {gb.x * dt, gb.y * dt, gb.z * dt};
       L.dt = dt;
+#if RBIS_FAST_SERIAL >= 2
+      L.Rd[0] = R00 * dt; L.Rd[1] = R01 * dt; L.Rd[2] = R02 * dt;
+      L.Rd[3] = R10 * dt; L.Rd[4] = R11 * dt; L.Rd[5] = R12 * dt;
+      L.Rd[6] = R20 * dt; L.Rd[7] = R21 * dt; L.Rd[8] = R22 * dt;
+#else
       {
         const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
         const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
@@ -1237,6 +1346,7 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         L.Rd[3] = (txy + twz) * dt;       L.Rd[4] = (1 - (txx + tzz)) * dt; L.Rd[5] = (tyz - twx) * dt;
         L.Rd[6] = (txz - twy) * dt;       L.Rd[7] = (tyz + twx) * dt;       L.Rd[8] = (1 - (txx + tyy)) * dt;
       }
+#endif
 #if RBIS_PARK_STATE == 2
       park_state<PARK_COV>(P, s);
 #elif RBIS_PARK_STATE
@@ -1272,7 +1382,7 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         s.ll = pk.d[9];
       }
 #endif
-      state_propagate(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
+      state_propagate<(RBIS_FAST_SERIAL >= 2)>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
     } else if (op.kind == 1) {
       // ---- indexed / indexed-plus-orientation measurement ----
       const StreamDesc& st = p.streams[op.stream];
