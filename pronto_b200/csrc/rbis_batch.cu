@@ -24,7 +24,8 @@
 #undef RBIS_LATE_LOADS
 #define RBIS_LATE_LOADS 1
 #undef RBIS_PARK_STATE
-#define RBIS_PARK_STATE 2   // 168 registers per thread: the filter state waits in spare tensor memory during the sweeps
+#define RBIS_PARK_STATE 2   // 168 registers per thread: the filter state waits in spare tensor memory during a measurement sweep
+#define RBIS_PARK_COV_KEEP 0x3ffffffu  // ... and stays in registers during the covariance step (no spills either way, fewer TMEM ops)
 #include "rbis_kernels.cuh"
 #undef rbisk
 #include "rbis_stats.cuh"

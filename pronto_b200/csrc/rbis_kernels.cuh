@@ -866,10 +866,17 @@ __device__ __forceinline__ void unpark_state(const Cov& P, FilterState& s) {
     if constexpr ((MASK >> k) & 1u) state_field(s, k) = tm_settle(lo[k], hi[k]);
   });
 }
-constexpr uint32_t PARK_ALL = (1u << 26) - 1;
+constexpr uint32_t PARK_EVERYTHING = (1u << 26) - 1;
+#ifndef RBIS_PARK_MEAS_KEEP
+#define RBIS_PARK_MEAS_KEEP 0u   // fields that stay in registers during a measurement sweep (bit mask, dev knob)
+#endif
+#ifndef RBIS_PARK_COV_KEEP
+#define RBIS_PARK_COV_KEEP 0u    // fields that stay in registers during the covariance step (bit mask, dev knob)
+#endif
+constexpr uint32_t PARK_ALL = PARK_EVERYTHING & ~(uint32_t)(RBIS_PARK_MEAS_KEEP);
 // during the covariance step: v, chi, p, b_g, b_a, quaternion, log-likelihood (omega and a are rewritten by the state
 // step that follows; the linearisation point is already in Lin)
-constexpr uint32_t PARK_COV = PARK_ALL & ~(0x7u | (0x7u << 12));
+constexpr uint32_t PARK_COV = PARK_EVERYTHING & ~(0x7u | (0x7u << 12)) & ~(uint32_t)(RBIS_PARK_COV_KEEP);
 
 // x[idx] with a runtime (warp-uniform) index: select chain, registers cannot be indexed dynamically
 __device__ __forceinline__ double pick_state(const double (&x)[NS], int idx) {
