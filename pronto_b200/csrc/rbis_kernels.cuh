@@ -1,18 +1,18 @@
-// rbis_kernels.cuh -- sm_100a FP64 device code of the batched RBIS EKF hot path (v2).
+// rbis_kernels.cuh -- sm_100a FP64 device code of the batched RBIS EKF hot path.
 //
-// Mapping: ONE LANE PER FILTER, 256 filters per CTA, one CTA per SM (8 warps, two
-// per scheduler).  A filter's 21x21 covariance is kept symmetric-packed (231 doubles) and stays on
-// chip for the whole fused program, split over two memories that are read concurrently:
-//   * SHARED MEMORY: 113 slots as Ps[slot][lane] (conflict free, 226 KB per CTA) -- the 15x15 "active"
-//     part (rows/columns of v, chi, p, b_g, b_a), which is touched 5.5 times per slot and step;
-//   * TENSOR MEMORY: the other 118 slots (everything coupled to the angular-velocity / acceleration
-//     rows, touched 2-3 times per step, plus the (b_a,b_a) block).  Each thread owns 128 doubles of
-//     TMEM (its lane of the warp's 32-lane quarter, 256 32-bit columns) reached with
-//     tcgen05.ld/st.32x32b.x2; fetches are software pipelined (loads of column k+1 in flight while
-//     column k is computed).  RBIS_PLACEMENT=0 swaps the two roles.
-// State (21+4), log-likelihood and linearisation live in registers.  Per-op inputs (IMU rows,
-// measurement rows) are coalesced structure-of-arrays loads issued at the top of each op and
-// consumed at its end.  No cross-lane communication, no barriers: filters are independent.
+// Mapping: ONE LANE PER FILTER, one CTA per SM.  A filter's 21x21 covariance is kept symmetric-packed
+// and stays on chip for the whole fused program, split over two memories that are read concurrently: SHARED MEMORY as
+// Ps[slot][lane] (conflict free) and TENSOR MEMORY, of which each thread owns its lane of the warp's 32-lane quarter,
+// reached with tcgen05.ld/st.32x32b.x2; fetches are software pipelined (loads of column k+1 in flight while column k is
+// computed).  The file is compiled in two configurations (rbis_batch.cu includes it twice, into two namespaces):
+//   * dense    (RBIS_TPB 256, RBIS_PLACEMENT 1): all 231 slots on chip -- 113 in shared memory (the 15x15 "active" part:
+//     rows/columns of v, chi, p, b_g, b_a, touched 5.5 times per slot and step), 118 in tensor memory (everything coupled
+//     to the angular-velocity / acceleration rows, touched 2-3 times per step, plus the (b_a,b_a) block); 8 warps;
+//   * decoupled (RBIS_TPB 384, RBIS_PLACEMENT 2, kernels with DC = true): only the 120 active slots exist -- 75 in shared
+//     memory, the 9x9 block of (p, b_g, b_a) in tensor memory; 12 warps at 168 registers, the filter state parked in
+//     spare tensor memory during measurement sweeps.  See "decoupled filters" below.
+// State (21+4), log-likelihood and linearisation live in registers.  Per-op inputs (IMU rows, measurement rows) are
+// coalesced structure-of-arrays loads.  No cross-lane communication, no barriers: filters are independent.
 //
 // Reference semantics restated (paths under /root/reference/state-estimator/src/mav_state_est/):
 //   cov_propagate()  = insUpdateCovariance + getIMUProcessLinearizationContinuous  rbis.cpp:12-35,77-122
