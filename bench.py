@@ -43,11 +43,11 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 # committed under profiles/ (r1_ncu_full_v2*_instmix.csv: warp-level DFMA / DMUL / DADD per warp-step)
 # keyed by kernel variant (rbis_batch_last_kernel_variant): 0 dense, 2 decoupled
 EXECUTED = {0: {"dfma": 1546.79, "dmul": 132.95, "dadd": 127.98, "source": "profiles/r1_ncu_full_v3dense_bench_instmix.csv"},
-            2: {"dfma": 1090.2, "dmul": 120.7, "dadd": 107.1, "source": "profiles/r1_ncu_full_v3dc_bench_instmix.csv"}}
+            2: {"dfma": 1097.97, "dmul": 112.89, "dadd": 99.25, "source": "profiles/r1_ncu_full_v3dc_bench_instmix.csv"}}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused launch of this workload (65,536 filters x 200 steps), from the
 # ncu --set full capture of `bench.py --steps 3 --warmup 3` summarised in profiles/r1_ncu_full_v2d_bench_summary.csv
 NCU_TRAFFIC = {0: {"filters": 65_536, "chunk_steps": 200, "bytes": 942.367744e6 + 92.981504e6},  # r1_ncu_full_v3dense_bench_summary.csv
-               2: {"filters": 65_536, "chunk_steps": 200, "bytes": 883.828480e6 + 70.622208e6}}  # profiles/r1_ncu_full_v3dc_bench_summary.csv
+               2: {"filters": 65_536, "chunk_steps": 200, "bytes": 883.725824e6 + 74.453760e6}}  # profiles/r1_ncu_full_v3dc_bench_summary.csv
 VARIANT_NAME = {0: "dense (whole 21x21 covariance on chip, 256 filters per SM)", 1: "dense + general measurement path",
                 2: "decoupled (15x15 active block on chip, 384 filters per SM; chosen at run time because every filter's "
                    "omega / a covariance couplings are exactly zero, bit-identical to dense)"}

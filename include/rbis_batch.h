@@ -78,7 +78,7 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal */
   int32_t launch_groups;   /* fused launches are split into this many CTA ranges on separate streams so that
                               consecutive rbis_batch_run_fused calls overlap and the last, partially filled wave of
-                              one launch does not idle SMs; 0 = automatic (4 when the CTAs do not fill whole
+                              one launch does not idle SMs; 0 = automatic (6 when the CTAs do not fill whole
                               waves, else 1), 1 = off, max 8 */
   int32_t dense_only;      /* 0 (default) = automatic: fused programs run the "decoupled" kernel variant (only the
                               15x15 block of v, chi, p, b_g, b_a on chip, 384 filters per SM) whenever every filter's

@@ -1054,7 +1054,11 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   static_for<NC>([&](auto cc) {
     constexpr int c = cc;
     constexpr int xc = DC ? act_col(c) : c;
+#if RBIS_FAST_SERIAL >= 2
+    s.x[xc] = fma(Y[0][c], u0, fma(Y[1][c], u1, fma(Y[2][c], u2, s.x[xc])));
+#else
     s.x[xc] += fma(Y[0][c], u0, fma(Y[1][c], u1, Y[2][c] * u2));
+#endif
   });
   s.ll += -logdet - fma(e2, u2, fma(e1, u1, e0 * u0));
 }
