@@ -186,21 +186,25 @@ int main_stream_work(rbis_batch* h) {
   return 0;
 }
 
-// Split the m rows of a measurement into consecutive chunks along which R is block diagonal, then
-// merge neighbours greedily up to 3 rows (the register-resident fast path).  Blocks wider than 3
-// stay whole and take the general path.
-// chunk_fast: a 3-row chunk on an aligned index triple (3k, 3k+1, 3k+2) takes the unrolled meas3<I0> path.
+// Split the m rows of a measurement into consecutive chunks along which R is block diagonal (the finest such blocks).
+// Three consecutive one-row blocks on an aligned index triple (3k, 3k+1, 3k+2) are merged into one chunk for the unrolled
+// meas3<I0> path; every other one-row block is a chunk of its own for the scalar path meas1 (chunk_fast = 100 + index);
+// blocks of two or more correlated rows that are not an aligned triple take the general path.
 void mark_fast_chunks(rbisk::StreamDesc& d, bool* needs_general) {
   for (int c = 0; c < d.n_chunks; c++) {
     const int a0 = d.chunk_start[c];
-    const bool fast = d.chunk_len[c] == 3 && d.idx[a0] % 3 == 0 && d.idx[a0 + 1] == d.idx[a0] + 1 && d.idx[a0 + 2] == d.idx[a0] + 2;
-    d.chunk_fast[c] = fast ? d.idx[a0] : -1;
-    if (!fast) *needs_general = true;
+    const bool triple = d.chunk_len[c] == 3 && d.idx[a0] % 3 == 0 && d.idx[a0 + 1] == d.idx[a0] + 1 && d.idx[a0 + 2] == d.idx[a0] + 2;
+    if (triple) d.chunk_fast[c] = d.idx[a0];
+    else if (d.chunk_len[c] == 1) d.chunk_fast[c] = 100 + d.idx[a0];
+    else {
+      d.chunk_fast[c] = -1;
+      *needs_general = true;
+    }
   }
 }
 
 void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) {
-  std::vector<int> cut;  // start indices of finest blocks
+  std::vector<int> cut;  // start indices of the finest blocks
   cut.push_back(0);
   for (int k = 1; k < m; k++) {
     bool sep = true;
@@ -213,20 +217,21 @@ void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) 
   }
   cut.push_back(m);
   d.n_chunks = 0;
-  int start = 0, len = 0;
-  for (size_t i = 0; i + 1 < cut.size(); i++) {
-    const int blen = cut[i + 1] - cut[i];
-    if (len > 0 && len + blen > 3) {
-      d.chunk_start[d.n_chunks] = start;
-      d.chunk_len[d.n_chunks++] = len;
-      len = 0;
+  auto aligned_triple = [&](int a) {
+    return d.idx[a] % 3 == 0 && d.idx[a + 1] == d.idx[a] + 1 && d.idx[a + 2] == d.idx[a] + 2;
+  };
+  for (size_t i = 0; i + 1 < cut.size();) {
+    const int a = cut[i], blen = cut[i + 1] - cut[i];
+    // three one-row blocks in a row on an aligned index triple -> one chunk
+    if (blen == 1 && i + 3 < cut.size() && cut[i + 2] - cut[i + 1] == 1 && cut[i + 3] - cut[i + 2] == 1 && aligned_triple(a)) {
+      d.chunk_start[d.n_chunks] = a;
+      d.chunk_len[d.n_chunks++] = 3;
+      i += 3;
+      continue;
     }
-    if (len == 0) start = cut[i];
-    len += blen;
-  }
-  if (len > 0) {
-    d.chunk_start[d.n_chunks] = start;
-    d.chunk_len[d.n_chunks++] = len;
+    d.chunk_start[d.n_chunks] = a;
+    d.chunk_len[d.n_chunks++] = blen;
+    i += 1;
   }
 }
 

@@ -467,8 +467,9 @@ struct Buf {
   double d[N];
   uint32_t lo[N], hi[N];
 };
-template <class L>
-__device__ __forceinline__ void issue(const Cov& P, Buf<L::N>& b) {
+template <class L, int NB>
+__device__ __forceinline__ void issue(const Cov& P, Buf<NB>& b) {
+  static_assert(NB >= L::N, "buffer too small for the fetch list");
   static_for<L::N>([&](auto kc) {
     constexpr int k = kc;
     constexpr int i = L::row(k) < L::col(k) ? L::row(k) : L::col(k), j = L::row(k) < L::col(k) ? L::col(k) : L::row(k);
@@ -489,8 +490,8 @@ __host__ __device__ constexpr bool any_tm() {
   }
   return any;
 }
-template <class L>
-__device__ __forceinline__ void commit(Buf<L::N>& b) {
+template <class L, int NB>
+__device__ __forceinline__ void commit(Buf<NB>& b) {
   if constexpr (any_tm<L>()) tm_wait_ld();
   static_for<L::N>([&](auto kc) {
     constexpr int k = kc;
@@ -1063,6 +1064,78 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   s.ll += -logdet - fma(e2, u2, fma(e1, u1, e0 * u0));
 }
 
+// meas1: a ONE-ROW chunk on any state index (yaw lock, vicon yaw, altimeter-style updates; and every row of an index set
+// that is not an aligned triple when its noise is uncorrelated with the other rows).  The index is a run-time, warp-uniform
+// value: the row P[idx, :] is fetched with run-time addressing (15 or 21 loads), everything after that -- the rank-1
+// sweep P -= h h^T / s and the state update -- runs over compile-time slots with h in registers.
+template <bool DC>
+__device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& st, int a0, int idx, long long row, long long N,
+                                      long long n, long long sn, const V3& dquat, const V3& chi0) {
+  constexpr int NC = DC ? N_ACT : NS;
+  constexpr auto pos = &carried_pos<DC>;
+  const double z = ldg_early(st.z + (row * st.m + a0) * st.cols + sn);
+  const double Rv = (st.r_mode == 1) ? ldg_early(st.R + (long long)a0 * N + n) : __ldg(st.R + a0 + (long long)st.m * a0);
+  double h[NC];
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int col = DC ? act_col(c) : c;
+    h[c] = P.getr(idx, col);
+  });
+  // h[pos(idx)] and x[idx] by select chains (registers cannot be indexed at run time)
+  double hii = h[0];
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int col = DC ? act_col(c) : c;
+    if (c > 0) hii = (idx == col) ? h[c] : hii;
+  });
+  const double sv = Rv + hii;
+  const double r = 1.0 / sv;
+  {
+    constexpr int TS = RBIS_SWEEP_TILE;
+    constexpr int NSW = kSweepLen<DC>;
+    constexpr int NT = (NSW + TS - 1) / TS;
+    Buf<TS> b0, b1;
+    issue<SweepRun<DC, 0, (NSW < TS ? NSW : TS)>>(P, b0);
+    static_for<NT>([&](auto tc) {
+      constexpr int t = tc;
+      constexpr int s0 = t * TS;
+      constexpr int len = (NSW - s0) < TS ? (NSW - s0) : TS;
+      using Cur = SweepRun<DC, s0, len>;
+      auto& cur = pick<t % 2>(b0, b1);
+      auto& nxt = pick<(t + 1) % 2>(b0, b1);
+      commit<Cur>(cur);
+      if constexpr (t + 1 < NT) {
+        constexpr int s1 = s0 + TS;
+        constexpr int len1 = (NSW - s1) < TS ? (NSW - s1) : TS;
+        issue<SweepRun<DC, s1, len1>>(P, nxt);
+      }
+      static_for<len>([&](auto kc) {
+        constexpr int k = kc;
+        constexpr int i = Cur::row(k), j = Cur::col(k);
+        P.template set<i, j>(fma(-h[pos(i)], h[pos(j)] * r, cur.d[k]));
+      });
+      RBIS_SCHED_FENCE();
+    });
+  }
+  tm_wait_st();
+  double rr;
+  if (st.has_orient && idx >= 6 && idx <= 8) {
+    const int k = idx - 6;
+    const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
+    const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
+    rr = dq - (pick_state(s.x, idx) - c0);
+  } else {
+    rr = z - pick_state(s.x, idx);
+  }
+  const double u = rr * r;
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int xc = DC ? act_col(c) : c;
+    s.x[xc] = fma(h[c], u, s.x[xc]);
+  });
+  s.ll += -log(sv) - rr * u;
+}
+
 // General chunk (any M <= 9, any indices): same mathematics, compact loops, run-time element access,
 // HP in local memory.  Correctness path for index sets that are not aligned triples.
 struct GenResult {
@@ -1418,7 +1491,9 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
           case 15: meas3<15, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           case 18: meas3<18, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           default:
-            if constexpr (GENERAL) {
+            if (fast >= 100) {  // one-row chunk on state index fast - 100
+              meas1<DC>(P, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
+            } else if constexpr (GENERAL) {
               double xs[NS];
 #pragma unroll
               for (int c = 0; c < NS; c++) xs[c] = s.x[c];

@@ -127,6 +127,45 @@ def test_measuring_omega_couples_the_filters_and_later_launches_go_dense():
     assert np.any(c[0:3, 3:6] != 0)  # the couplings did become non-zero
 
 
+def test_scalar_updates_stay_on_the_decoupled_kernel_and_match_dense_and_oracle(oracle):
+    """One-row chunks (yaw lock [17, 8] with orientation, rbis_yawlock_update.cpp:97-99; a plain scalar on the yaw bias,
+    :79; an unaligned diagonal triple) take meas1 and do not need the general path."""
+    N, T = 260, 60
+    sc = scenario(N, T, tumbling=True)
+    st = sc["st"]
+    rng = np.random.default_rng(12)
+    n_extra = T // 5
+    yaw_z = np.ascontiguousarray(rng.normal(size=(n_extra, 2, N)) * 1e-3)
+    yaw_q = np.ascontiguousarray(st["pose_q"][:1].repeat(n_extra, axis=0))
+    bias_z = np.ascontiguousarray(rng.normal(size=(n_extra, 1, N)) * 1e-3)
+    odd_z = np.ascontiguousarray(rng.normal(size=(n_extra, 3, N)) * 0.05)
+    extra = [dict(idx=[17, 8], z=yaw_z, R=np.diag([1e-4, 1e-2]), quat=yaw_q),
+             dict(idx=[17], z=bias_z, R=np.array([[1e-4]])),
+             dict(idx=[4, 5, 9], z=odd_z, R=np.diag([0.02, 0.03, 0.04]))]
+    ev, k = [], 0
+    for e in st["events"]:
+        ev.append(e)
+        if e[0] == capi.OP_IMU and (e[2] % 5) == 4 and k < n_extra:
+            for sidx in (2, 3, 4):
+                ev.append((capi.OP_MEAS, sidx, k, e[3], 0.0))
+            k += 1
+    gs = gpu_streams(st) + [MeasStream(x["idx"], x["z"], x["R"], quat=x.get("quat")) for x in extra]
+    out = []
+    for dense_only in (False, True):
+        with RBISBatch(N, dense_only=dense_only) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            b.run_fused(ev, imu=st["imu"], streams=gs)
+            out.append((b.get_state(), b.last_kernel_variant))
+    assert out[0][1] == DECOUPLED and out[1][1] == DENSE
+    _same(out[0][0], out[1][0])
+    orc = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st) + extra, ev,
+                              n_threads=NTHREADS)
+    got = out[0][0]
+    assert np.max(np.abs(got[0] - orc["vec"])) < 1e-9 and np.max(np.abs(got[2] - orc["cov"])) < 1e-11
+    assert np.max(np.abs(got[3] - orc["loglik"]) / np.maximum(1.0, np.abs(orc["loglik"]))) < 1e-9
+
+
 def _delayed_program(sc, n_slots=3, lat=50):
     ev = sc["st"]["events"]
     pose = [e for e in ev if e[0] == 1 and e[1] == 1]
