@@ -14,8 +14,12 @@ rows (all chunks of the run are resident in HBM, far larger than L2), the state 
             its inputs host->device and reads the per-chunk statistics back.
   roofline  fused kernel only: algorithmic FP64 flops / mean launch time, against the
             DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
-  cpu_baseline  the CPU oracle (restatement of the reference; the reference itself cannot be built
-            here) on all host threads, bounded sample.
+  cpu_baseline  the CPU oracle (restatement of the reference, pinned to the reference's own compiled
+            sources -- DESIGN.md 2) on all host threads, bounded sample.
+  informational legs in the same line: dense_variant (the dense kernel on the same launches + a bit-identity
+            check against the headline run), sweep_shared_inputs (parameter sweep over shared input columns,
+            end to end), next_rows (notch cascade against the HBM roofline, EKF smoother backward pass).
+  config.kernel_variant says which fused kernel the library chose (decoupled / dense, include/rbis_batch.h).
 --impl reference times that CPU path alone on the same workload shape.
 """
 import argparse
