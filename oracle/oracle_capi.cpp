@@ -137,6 +137,7 @@ static int64_t run_ensemble_impl(int64_t Nf, int n_threads, double* vec, double*
                          int64_t n_events, const orc_event_t* events, int64_t history_span, double* trace_vec,
                          double* trace_quat, double* trace_cov, double* trace_loglik, double smooth_dt,
                          double* post_vec, double* post_quat, double* post_cov) {
+  (void)n_streams;
   std::atomic<int64_t> next(0), calls(0);
   auto worker = [&]() {
     int64_t my_calls = 0;
