@@ -52,7 +52,7 @@ EXECUTED = {0: {"dfma": 1546.79, "dmul": 132.95, "dadd": 127.98, "source": "prof
 # ncu --set full capture of `bench.py --steps 3 --warmup 3` summarised in profiles/r1_ncu_full_v2d_bench_summary.csv
 NCU_TRAFFIC = {0: {"filters": 65_536, "chunk_steps": 200, "bytes": 942.367744e6 + 92.981504e6},  # r1_ncu_full_v3dense_bench_summary.csv
                2: {"filters": 65_536, "chunk_steps": 200, "bytes": 883.725824e6 + 74.453760e6}}  # profiles/r1_ncu_full_v3dc_bench_summary.csv
-VARIANT_NAME = {0: "dense (whole 21x21 covariance on chip, 256 filters per SM)", 1: "dense + general measurement path",
+VARIANT_NAME = {0: "dense (whole 21x21 covariance on chip, 256 filters per SM)", 1: "dense + correlated-block measurement path",
                 2: "decoupled (15x15 active block on chip, 384 filters per SM; chosen at run time because every filter's "
                    "omega / a covariance couplings are exactly zero, bit-identical to dense)"}
 

@@ -19,7 +19,11 @@ ch = bench.device_chunk(truth, 0, T, N, gen, dev)
 p = synth.NOMINAL
 R_lego = np.eye(3) * p["r_vxyz"] ** 2
 yaw_z = torch.zeros((T // 10, 1, N), dtype=torch.float64, device=dev)
-for label, with_yaw in (("IMU + leg odometry", False), ("IMU + leg odometry + scalar yaw update every 10th step", True)):
+ql_z = torch.zeros((T // 10, 4, N), dtype=torch.float64, device=dev)
+Bq = np.random.default_rng(3).normal(size=(4, 4))
+R_ql = Bq @ Bq.T * 1e-3 + np.eye(4) * 1e-2   # correlated 4x4: quick-lock style [8, 9, 10, 11] (quick_lock.cpp:132) -> meas_general
+for label, with_yaw in (("IMU + leg odometry", False), ("IMU + leg odometry + scalar yaw update every 10th step", True),
+                        ("IMU + leg odometry + correlated 4-row update [8,9,10,11] every 10th step (general path)", 2)):
     ev, li, yi = [], 0, 0
     for k in range(T):
         ut = (k + 1) * 1000
@@ -28,7 +32,9 @@ for label, with_yaw in (("IMU + leg odometry", False), ("IMU + leg odometry + sc
         if with_yaw and k % 10 == 0: ev.append((capi.OP_MEAS, 1, yi, ut, 0.0)); yi += 1
     ops = make_ops(ev)
     streams = [MeasStream(synth.LEGODO_IDX, ch["legodo"], R_lego)]
-    if with_yaw:
+    if with_yaw == 2:
+        streams.append(MeasStream([8, 9, 10, 11], ql_z, R_ql))
+    elif with_yaw:
         streams.append(MeasStream([8], yaw_z, np.array([[0.01]])))
     with RBISBatch(N) as b:
         b.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])

@@ -84,8 +84,8 @@ typedef struct {
                               15x15 block of v, chi, p, b_g, b_a on chip, 384 filters per SM) whenever every filter's
                               covariance couplings to the omega / a rows are exactly zero -- true for every filter
                               started from the reference's diagonal initial covariance (MSE/rbis_initializer.cpp:85-91)
-                              until a measurement indexes omega or a -- and the program has only aligned-triple
-                              measurement chunks on other indices; results are bit-identical to the dense variant.
+                              until a measurement indexes omega or a -- and no stream of the program indexes omega or a;
+                              results are bit-identical to the dense variant.
                               1 = always run the dense variant (whole covariance on chip, 256 filters per SM). */
 } rbis_batch_config_t;
 
@@ -128,8 +128,9 @@ int64_t rbis_batch_num_filters(const rbis_batch_t* h);
 void* rbis_batch_stream(rbis_batch_t* h);
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t rbis_batch_launch_count(const rbis_batch_t* h);
-/* Kernel variant the last rbis_batch_run_fused / single-op call launched: 0 dense, 1 dense with the general
- * measurement path, 2 decoupled (see rbis_batch_config_t::dense_only); -1 before the first launch. */
+/* Kernel variant the last rbis_batch_run_fused / single-op call launched: 0 dense, 2 decoupled (see
+ * rbis_batch_config_t::dense_only), +1 when the program has measurement chunks other than uncorrelated aligned index
+ * triples (the instantiations that also contain the one-row and the correlated-block updates); -1 before the first launch. */
 int rbis_batch_last_kernel_variant(const rbis_batch_t* h);
 
 /* ---- RBISResetUpdate::updateFilter (MSE/rbis_update_interface.cpp:23-28): posterior := given,

@@ -285,7 +285,7 @@ class RBISBatch:
 
     @property
     def last_kernel_variant(self):
-        """0 dense, 1 dense + general measurement path, 2 decoupled (rbis_batch_config_t::dense_only); -1 before any."""
+        """0 dense, 2 decoupled (rbis_batch_config_t::dense_only), +1 with correlated-row chunks; -1 before any launch."""
         return int(self.lib.rbis_batch_last_kernel_variant(self.h))
 
     @property

@@ -25,6 +25,7 @@
 #define RBIS_LATE_LOADS 1
 #undef RBIS_PARK_STATE
 #define RBIS_PARK_STATE 2   // 168 registers per thread: the filter state waits in spare tensor memory during a measurement sweep
+#undef RBIS_PARK_COV_KEEP
 #define RBIS_PARK_COV_KEEP 0x3ffffffu  // ... and stays in registers during the covariance step (no spills either way, fewer TMEM ops)
 #include "rbis_kernels.cuh"
 #undef rbisk
@@ -117,7 +118,7 @@ struct rbis_batch {
   double* d_notch_state = nullptr;  // [3][MAX_NOTCH][4][notch_cols]
   int64_t notch_cols = 0;
   DevBuf notch_stage;               // device copy of a host chunk
-  int last_variant = -1;  // kernel variant of the last fused launch: 0 dense, 1 dense + general measurements, 2 decoupled
+  int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
   DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
@@ -155,17 +156,21 @@ struct rbis_batch {
 namespace {
 
 constexpr int kSmemBytes = rbisk::SMEM_BYTES;
+// per stream in the shared-R device buffer: R (m x m column-major, 81), then for its correlated blocks the rows of
+// L_R^-1 ([9][9] row-major, absolute row numbers) and D_R ([9]) of R_block = L_R D_R L_R^T (rbisk::RS_W, RS_D)
+constexpr int kRShared = rbisk::RS_STRIDE;
 constexpr int kSmemBytesDc = rbisk_dc::SMEM_BYTES;
 
+// variant: bit 1 = decoupled, bit 0 = the program has measurement chunks other than aligned triples (meas1 / meas_block compiled in)
 void launch_variant(int variant, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
-  if (variant == 2) {
+  if (variant & 2) {
     rbisk_dc::KParams kd;
     std::memcpy(&kd, &kp, sizeof(kd));
-    rbisk_dc::rbis_fused_kernel<false, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
-  } else if (variant == 1) {
-    rbisk::rbis_fused_kernel<true><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+    if (variant & 1) rbisk_dc::rbis_fused_kernel<true, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
+    else rbisk_dc::rbis_fused_kernel<false, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
   } else {
-    rbisk::rbis_fused_kernel<false><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+    if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+    else rbisk::rbis_fused_kernel<false><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
   }
 }
 
@@ -195,12 +200,43 @@ void mark_fast_chunks(rbisk::StreamDesc& d, bool* needs_general) {
     const int a0 = d.chunk_start[c];
     const bool triple = d.chunk_len[c] == 3 && d.idx[a0] % 3 == 0 && d.idx[a0 + 1] == d.idx[a0] + 1 && d.idx[a0 + 2] == d.idx[a0] + 2;
     if (triple) d.chunk_fast[c] = d.idx[a0];
-    else if (d.chunk_len[c] == 1) d.chunk_fast[c] = 100 + d.idx[a0];
     else {
-      d.chunk_fast[c] = -1;
-      *needs_general = true;
+      d.chunk_fast[c] = d.chunk_len[c] == 1 ? 100 + d.idx[a0]   // one row: meas1
+                                            : -1;               // correlated rows: meas_block on the decorrelated rows
+      *needs_general = true;  // either lives in the BLOCKS kernel instantiations only
     }
   }
+}
+
+// R_block = L D L^T (unit lower L) of rows/columns a0..a0+len-1 of the m x m column-major R; writes the rows of L^-1 into
+// W[(a0+a)*9 + (a0+b)] and D into Dg[a0+a].  With z' = L^-1 z the block becomes `len` scalar measurements with
+// uncorrelated noise D, which the device applies one after the other (meas_block).
+int decorrelate_block(const double* R, int m, int a0, int len, double* W, double* Dg) {
+  double L[RBIS_MAX_MEAS][RBIS_MAX_MEAS] = {}, D[RBIS_MAX_MEAS] = {};
+  for (int k = 0; k < len; k++) {
+    double d = R[(a0 + k) + (size_t)m * (a0 + k)];
+    for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p] * D[p];
+    if (!(d > 0)) return fail(RBIS_ERR_INVALID, "measurement covariance block at row %d is not positive definite", a0);
+    D[k] = d;
+    L[k][k] = 1.0;
+    for (int i = k + 1; i < len; i++) {
+      double v = R[(a0 + i) + (size_t)m * (a0 + k)];
+      for (int p = 0; p < k; p++) v -= L[i][p] * L[k][p] * D[p];
+      L[i][k] = v / d;
+    }
+  }
+  // invert the unit lower triangle by forward substitution, column by column
+  for (int c = 0; c < len; c++) {
+    double x[RBIS_MAX_MEAS] = {};
+    for (int i = c; i < len; i++) {
+      double v = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; k++) v -= L[i][k] * x[k];
+      x[i] = v;
+    }
+    for (int i = c; i < len; i++) W[(a0 + i) * RBIS_MAX_MEAS + (a0 + c)] = x[i];
+  }
+  for (int k = 0; k < len; k++) Dg[a0 + k] = D[k];
+  return 0;
 }
 
 void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) {
@@ -351,9 +387,9 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (imu) {
     if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * (size_t)kp.imu_cols, mem, cst, &kp.imu)) return rc;
   }
-  std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * 81, 0.0);
+  std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * kRShared, 0.0);
   bool any_shared = false;
-  bool needs_general = false;  // some chunk is not an aligned triple -> kernel variant with the general path
+  bool needs_general = false;  // some chunk is not an aligned triple -> the kernel instantiations that contain meas1 / meas_block
   bool passive_index = false;  // some stream measures omega or a directly -> couplings become non-zero
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
@@ -372,8 +408,12 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (in.has_orientation)
       if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
     if (in.r_mode == RBIS_R_SHARED_FULL) {
-      std::memcpy(&rshared[(size_t)s * 81], in.R, sizeof(double) * in.m * in.m);
-      d.R = (grouped ? h->d_rshared_ring[ring] : h->d_rshared) + (size_t)s * 81;
+      double* rs = &rshared[(size_t)s * kRShared];
+      std::memcpy(rs, in.R, sizeof(double) * in.m * in.m);
+      for (int c = 0; c < d.n_chunks; c++)
+        if (d.chunk_fast[c] == -1)
+          if (int rc = decorrelate_block(in.R, in.m, d.chunk_start[c], d.chunk_len[c], rs + rbisk::RS_W, rs + rbisk::RS_D)) return rc;
+      d.R = (grouped ? h->d_rshared_ring[ring] : h->d_rshared) + (size_t)s * kRShared;
       any_shared = true;
     } else {
       if (int rc = copy_in(h, slot.rdiag[s], in.R, (size_t)in.m * N, mem, cst, &d.R)) return rc;
@@ -382,7 +422,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
   // ---- kernel variant ----
   int variant = needs_general ? 1 : 0;
-  const bool dc_eligible = !h->cfg.dense_only && !needs_general && !passive_index && restores_ok;
+  const bool dc_eligible = !h->cfg.dense_only && !passive_index && restores_ok;
   if (dc_eligible && h->decoupled < 0) {
     // one device pass over the couplings, then a host read: happens once after set_state / set_filter, not per launch
     if (int rc = main_stream_work(h)) return rc;
@@ -395,8 +435,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->decoupled = flag ? 0 : 1;
   }
-  if (dc_eligible && h->decoupled == 1) variant = 2;
-  const int tpb = variant == 2 ? rbisk_dc::TPB : rbisk::TPB;
+  if (dc_eligible && h->decoupled == 1) variant |= 2;
+  const int tpb = (variant & 2) ? rbisk_dc::TPB : rbisk::TPB;
   const unsigned grid = (unsigned)((N + tpb - 1) / tpb);
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
@@ -467,12 +507,12 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   // ---- what the launch leaves behind ----
   // A dense launch keeps exact zeros exact unless it measured omega / a or restored a slot of unknown content.
   const int before = h->decoupled;
-  if (variant != 2) {
+  if (!(variant & 2)) {
     if (passive_index) h->decoupled = 0;
     else if (!restores_ok) h->decoupled = -1;
   }
   if (any_snapshot) {
-    const char as_launch = (variant == 2 || (before == 1 && !passive_index && restores_ok)) ? 1 : 0;
+    const char as_launch = ((variant & 2) || (before == 1 && !passive_index && restores_ok)) ? 1 : 0;
     for (auto& f : snap_dc)
       if (f == 2) f = as_launch;
   }
@@ -559,7 +599,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     for (int r = 0; r < rbis_batch::kRing; r++) {
       CREATE_TRY(cudaEventCreateWithFlags(&h->uploaded[r], cudaEventDisableTiming));
       for (int g = 0; g < h->n_groups; g++) CREATE_TRY(cudaEventCreateWithFlags(&h->gdone[r][g], cudaEventDisableTiming));
-      CREATE_TRY(cudaMalloc(&h->d_rshared_ring[r], (size_t)RBIS_MAX_STREAMS * 81 * sizeof(double)));
+      CREATE_TRY(cudaMalloc(&h->d_rshared_ring[r], (size_t)RBIS_MAX_STREAMS * kRShared * sizeof(double)));
     }
   }
   for (auto& s : h->slots) {
@@ -572,7 +612,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   CREATE_TRY(cudaMalloc(&h->P, N * rbisk::NP * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->loglik, N * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->qparams, N * 4 * sizeof(double)));
-  CREATE_TRY(cudaMalloc(&h->d_rshared, (size_t)RBIS_MAX_STREAMS * 81 * sizeof(double)));
+  CREATE_TRY(cudaMalloc(&h->d_rshared, (size_t)RBIS_MAX_STREAMS * kRShared * sizeof(double)));
   if (c.snapshot_slots > 0) {
     CREATE_TRY(cudaMalloc(&h->snap, (size_t)c.snapshot_slots * rbisk::SNAP_ROWS * N * sizeof(double)));
     h->snap_valid.assign((size_t)c.snapshot_slots, 0);
@@ -581,8 +621,9 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   CREATE_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rbisk::SMOOTH_SMEM_BYTES));
   CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
-  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   // default state: zeros, identity quaternion, zero covariance, zero process noise
   CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
   CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));

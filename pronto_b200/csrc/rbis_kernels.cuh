@@ -75,6 +75,9 @@
 // RBIS_ONE_LOG 1:     log of the determinant, as the reference writes it (rbis.cpp:142), instead of the sum of the
 //                     logs of the three pivots.
 // Measured (dev/kbench, 113,664 filters): 5.93 -> 6.10 (ONE_LOG) -> 6.44 (FAST_SERIAL 1) -> 6.78 G filter-steps/s (2).
+#ifndef RBIS_MEAS1_GETR
+#define RBIS_MEAS1_GETR 0
+#endif
 #ifndef RBIS_FAST_SERIAL
 #define RBIS_FAST_SERIAL 2
 #endif
@@ -100,6 +103,8 @@ constexpr int MAX_MEAS = 9;
 constexpr int MAX_STREAMS = 8;
 constexpr int MAX_CHUNKS = 9;
 constexpr int SNAP_ROWS = 257;  // 21 vec + 4 quat + loglik + 231 covariance
+// shared-R buffer of a stream: R (81 doubles), rows of L_R^-1 (81), D_R (9) -- see rbis_batch.cu decorrelate_block
+constexpr int RS_W = 81, RS_D = 162, RS_STRIDE = 171;
 
 __host__ __device__ constexpr int slot(int i, int j) { return i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j; }
 
@@ -1064,6 +1069,74 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   s.ll += -logdet - fma(e2, u2, fma(e1, u1, e0 * u0));
 }
 
+// Row idx (run time, warp uniform) of the covariance over the carried columns: all loads issued, ONE tensor-memory wait.
+template <bool DC>
+__device__ __forceinline__ void fetch_row(const Cov& P, int idx, double (&row)[DC ? N_ACT : NS]) {
+  constexpr int NC = DC ? N_ACT : NS;
+  uint32_t lo[NC], hi[NC];
+  bool tm[NC];
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int col = DC ? act_col(c) : c;
+    const int s_ = slot(idx, col);
+    const int k = c_place.idx[s_];
+    tm[c] = c_place.tm[s_];
+    lo[c] = hi[c] = 0;
+    row[c] = 0.0;
+    if (tm[c]) tm_ld2(P.tm + 2 * k, lo[c], hi[c]);
+    else row[c] = P.Ps[sm_off(k)];
+  });
+  tm_wait_ld();
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    const double v = tm_settle(lo[c], hi[c]);
+    row[c] = tm[c] ? v : row[c];
+  });
+}
+// g[pos(idx)] for a run-time index (select chain)
+template <bool DC>
+__device__ __forceinline__ double pick_carried(const double (&g)[DC ? N_ACT : NS], int idx) {
+  constexpr int NC = DC ? N_ACT : NS;
+  double v = g[0];
+  static_for<NC>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int col = DC ? act_col(c) : c;
+    if (c > 0) v = (idx == col) ? g[c] : v;
+  });
+  return v;
+}
+// P -= g g^T r over the carried slots, pipelined tiles
+template <bool DC>
+__device__ __forceinline__ void rank1_sweep(Cov& P, const double (&g)[DC ? N_ACT : NS], double r) {
+  constexpr auto pos = &carried_pos<DC>;
+  constexpr int TS = RBIS_SWEEP_TILE;
+  constexpr int NSW = kSweepLen<DC>;
+  constexpr int NT = (NSW + TS - 1) / TS;
+  Buf<TS> b0, b1;
+  issue<SweepRun<DC, 0, (NSW < TS ? NSW : TS)>>(P, b0);
+  static_for<NT>([&](auto tc) {
+    constexpr int t = tc;
+    constexpr int s0 = t * TS;
+    constexpr int len = (NSW - s0) < TS ? (NSW - s0) : TS;
+    using Cur = SweepRun<DC, s0, len>;
+    auto& cur = pick<t % 2>(b0, b1);
+    auto& nxt = pick<(t + 1) % 2>(b0, b1);
+    commit<Cur>(cur);
+    if constexpr (t + 1 < NT) {
+      constexpr int s1 = s0 + TS;
+      constexpr int len1 = (NSW - s1) < TS ? (NSW - s1) : TS;
+      issue<SweepRun<DC, s1, len1>>(P, nxt);
+    }
+    static_for<len>([&](auto kc) {
+      constexpr int k = kc;
+      constexpr int i = Cur::row(k), j = Cur::col(k);
+      P.template set<i, j>(fma(-g[pos(i)], g[pos(j)] * r, cur.d[k]));
+    });
+    RBIS_SCHED_FENCE();
+  });
+  tm_wait_st();
+}
+
 // meas1: a ONE-ROW chunk on any state index (yaw lock, vicon yaw, altimeter-style updates; and every row of an index set
 // that is not an aligned triple when its noise is uncorrelated with the other rows).  The index is a run-time, warp-uniform
 // value: the row P[idx, :] is fetched with run-time addressing (15 or 21 loads), everything after that -- the rank-1
@@ -1076,48 +1149,20 @@ __device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& 
   const double z = ldg_early(st.z + (row * st.m + a0) * st.cols + sn);
   const double Rv = (st.r_mode == 1) ? ldg_early(st.R + (long long)a0 * N + n) : __ldg(st.R + a0 + (long long)st.m * a0);
   double h[NC];
+#if RBIS_MEAS1_GETR
+  // element by element, blocking: keeps this rarely executed path small inside the common kernels
   static_for<NC>([&](auto cc) {
     constexpr int c = cc;
     constexpr int col = DC ? act_col(c) : c;
     h[c] = P.getr(idx, col);
   });
-  // h[pos(idx)] and x[idx] by select chains (registers cannot be indexed at run time)
-  double hii = h[0];
-  static_for<NC>([&](auto cc) {
-    constexpr int c = cc;
-    constexpr int col = DC ? act_col(c) : c;
-    if (c > 0) hii = (idx == col) ? h[c] : hii;
-  });
+#else
+  fetch_row<DC>(P, idx, h);
+#endif
+  const double hii = pick_carried<DC>(h, idx);
   const double sv = Rv + hii;
   const double r = 1.0 / sv;
-  {
-    constexpr int TS = RBIS_SWEEP_TILE;
-    constexpr int NSW = kSweepLen<DC>;
-    constexpr int NT = (NSW + TS - 1) / TS;
-    Buf<TS> b0, b1;
-    issue<SweepRun<DC, 0, (NSW < TS ? NSW : TS)>>(P, b0);
-    static_for<NT>([&](auto tc) {
-      constexpr int t = tc;
-      constexpr int s0 = t * TS;
-      constexpr int len = (NSW - s0) < TS ? (NSW - s0) : TS;
-      using Cur = SweepRun<DC, s0, len>;
-      auto& cur = pick<t % 2>(b0, b1);
-      auto& nxt = pick<(t + 1) % 2>(b0, b1);
-      commit<Cur>(cur);
-      if constexpr (t + 1 < NT) {
-        constexpr int s1 = s0 + TS;
-        constexpr int len1 = (NSW - s1) < TS ? (NSW - s1) : TS;
-        issue<SweepRun<DC, s1, len1>>(P, nxt);
-      }
-      static_for<len>([&](auto kc) {
-        constexpr int k = kc;
-        constexpr int i = Cur::row(k), j = Cur::col(k);
-        P.template set<i, j>(fma(-h[pos(i)], h[pos(j)] * r, cur.d[k]));
-      });
-      RBIS_SCHED_FENCE();
-    });
-  }
-  tm_wait_st();
+  rank1_sweep<DC>(P, h, r);
   double rr;
   if (st.has_orient && idx >= 6 && idx <= 8) {
     const int k = idx - 6;
@@ -1136,96 +1181,55 @@ __device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& 
   s.ll += -log(sv) - rr * u;
 }
 
-// General chunk (any M <= 9, any indices): same mathematics, compact loops, run-time element access,
-// HP in local memory.  Correctness path for index sets that are not aligned triples.
-struct GenResult {
-  double dx[NS];
-  double dll;
-};
-__device__ __noinline__ GenResult meas_general(int M, Cov P, const double* __restrict__ xs, int has_orient, int r_mode,
-                                               int m_stream, const int* __restrict__ idxs, const double* __restrict__ zrow,
-                                               long long zcols, long long sn, const double* __restrict__ Rp, int a0,
-                                               long long N, long long n, V3 dquat, V3 chi0) {
-  double HP[MAX_MEAS][NS], S[MAX_MEAS][MAX_MEAS], Lm[MAX_MEAS][MAX_MEAS], D[MAX_MEAS], r[MAX_MEAS], y[MAX_MEAS];
-  int idx[MAX_MEAS];
-  for (int a = 0; a < M; a++) idx[a] = idxs[a0 + a];
-  for (int a = 0; a < M; a++)
-    for (int c = 0; c < NS; c++) HP[a][c] = P.getr(idx[a], c);
-  for (int a = 0; a < M; a++)
-    for (int b = 0; b < M; b++) {
-      double rr;
-      if (r_mode == 1) rr = (a == b) ? __ldg(Rp + (long long)(a0 + a) * N + n) : 0.0;
-      else rr = __ldg(Rp + (a0 + a) + (long long)m_stream * (a0 + b));
-      S[a][b] = rr + HP[a][idx[b]];
-    }
-  double logdet = 0;
-  for (int k = 0; k < M; k++) {
-    double d = S[k][k];
-    for (int p = 0; p < k; p++) d -= Lm[k][p] * Lm[k][p] * D[p];
-    D[k] = d;
-    logdet += log(d);
-    for (int i = k + 1; i < M; i++) {
-      double v = S[i][k];
-      for (int p = 0; p < k; p++) v -= Lm[i][p] * Lm[k][p] * D[p];
-      Lm[i][k] = v / d;
-    }
-  }
-  // G = S^-1 HP by forward / diagonal / backward substitution, column by column
-  double G[MAX_MEAS][NS];
-  for (int c = 0; c < NS; c++) {
-    double w[MAX_MEAS];
-    for (int i = 0; i < M; i++) {
-      double v = HP[i][c];
-      for (int k = 0; k < i; k++) v -= Lm[i][k] * w[k];
-      w[i] = v;
-    }
-    for (int i = 0; i < M; i++) w[i] /= D[i];
-    for (int i = M - 1; i >= 0; i--) {
-      double v = w[i];
-      for (int k = i + 1; k < M; k++) v -= Lm[k][i] * w[k];
-      w[i] = v;
-    }
-    for (int i = 0; i < M; i++) G[i][c] = w[i];
-  }
-  for (int j = 0; j < NS; j++)
-    for (int i = 0; i <= j; i++) {
-      double acc = P.getr(i, j);
-      for (int a = 0; a < M; a++) acc -= HP[a][i] * G[a][j];
-      P.setr(i, j, acc);
-    }
+// meas_block: a chunk of M (2..9) rows with CORRELATED noise on any indices.  The host factors R_block = L D L^T; with
+// z' = L^-1 z, H' = L^-1 H the block is M scalar measurements with uncorrelated noise D, applied one after the other
+// (the same posterior and the same log-likelihood as the reference's single update, rbis.cpp:124-143, by the chain rule).
+// Row a of H' combines the covariance rows idx_b, b <= a, so everything lives in registers: g = P H'_a^T (15 / 21
+// doubles), a rank-1 sweep over compile-time slots, the state update.  No local-memory arrays, no separate kernel variant.
+// Only the BLOCKS = true kernel variants contain it.
+template <bool DC>
+__device__ __forceinline__ void meas_block(Cov& P, FilterState& s, const StreamDesc& st, int a0, int M, long long row, long long N,
+                                           long long n, long long sn, const V3& dquat, const V3& chi0) {
+  constexpr int NC = DC ? N_ACT : NS;
+  const double* W = st.R + RS_W;
+  const double* Dg = st.R + RS_D;
+  (void)N; (void)n;
   for (int a = 0; a < M; a++) {
-    const int k = idx[a] - 6;
-    const double xi = xs[idx[a]];
-    if (has_orient && k >= 0 && k <= 2) {
-      const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
-      const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
-      r[a] = dq - (xi - c0);
-    } else {
-      r[a] = __ldg(zrow + (long long)(a0 + a) * zcols + sn) - xi;
+    double g[NC];
+    static_for<NC>([&](auto cc) { g[cc] = 0.0; });
+    for (int b = 0; b <= a; b++) {
+      const double w = __ldg(W + (a0 + a) * MAX_MEAS + (a0 + b));
+      double rowv[NC];
+      fetch_row<DC>(P, st.idx[a0 + b], rowv);
+      static_for<NC>([&](auto cc) { g[cc] = fma(w, rowv[cc], g[cc]); });
     }
+    double sv = __ldg(Dg + a0 + a), rp = 0.0;
+    for (int b = 0; b <= a; b++) {
+      const double w = __ldg(W + (a0 + a) * MAX_MEAS + (a0 + b));
+      const int ib = st.idx[a0 + b];
+      sv = fma(w, pick_carried<DC>(g, ib), sv);
+      const double xi = pick_state(s.x, ib);
+      double rb;
+      if (st.has_orient && ib >= 6 && ib <= 8) {
+        const int k = ib - 6;
+        const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
+        const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
+        rb = dq - (xi - c0);
+      } else {
+        rb = __ldg(st.z + (row * st.m + (a0 + b)) * st.cols + sn) - xi;
+      }
+      rp = fma(w, rb, rp);
+    }
+    const double r = 1.0 / sv;
+    rank1_sweep<DC>(P, g, r);
+    const double u = rp * r;
+    static_for<NC>([&](auto cc) {
+      constexpr int c = cc;
+      constexpr int xc = DC ? act_col(c) : c;
+      s.x[xc] = fma(g[c], u, s.x[xc]);
+    });
+    s.ll += -log(sv) - rp * u;
   }
-  // y = S^-1 r
-  for (int i = 0; i < M; i++) {
-    double v = r[i];
-    for (int k = 0; k < i; k++) v -= Lm[i][k] * y[k];
-    y[i] = v;
-  }
-  for (int i = 0; i < M; i++) y[i] /= D[i];
-  for (int i = M - 1; i >= 0; i--) {
-    double v = y[i];
-    for (int k = i + 1; k < M; k++) v -= Lm[k][i] * y[k];
-    y[i] = v;
-  }
-  double quad = 0;
-  for (int a = 0; a < M; a++) quad += r[a] * y[a];
-  GenResult out;
-  for (int c = 0; c < NS; c++) {
-    double v = 0;
-    for (int a = 0; a < M; a++) v += HP[a][c] * y[a];
-    out.dx[c] = v;
-  }
-  out.dll = -logdet - quad;
-  return out;
 }
 
 // state half of rbisApplyDelta for a whole measurement op: dstate = RBIS(K r) then addState.
@@ -1303,17 +1307,18 @@ __device__ __forceinline__ void store_overwritten_blocks(double* __restrict__ ds
 
 // ------------------------------------------------------------------------------------------------
 // The fused kernel: every lane loads its filter, runs the whole op program, stores it back.
-// GENERAL = false is launched when every measurement chunk of every stream is an aligned triple.
+// BLOCKS = true variants also contain meas1 and meas_block (one-row chunks, chunks of correlated rows); they are launched
+// only for programs that have such chunks, so that the common program (aligned triples only) keeps its registers and
+// code layout: merely compiling the two paths into it costs 3-8 %.
 // ------------------------------------------------------------------------------------------------
 // DC = true is launched when the host has verified that every filter's omega / a couplings are exactly zero and no
-// measurement of the program indexes omega or a (see "decoupled filters" above); it implies GENERAL = false.
-template <bool GENERAL, bool DC = false>
+// measurement of the program indexes omega or a (see "decoupled filters" above).
+template <bool BLOCKS, bool DC = false>
 #ifdef RBIS_MAXNREG  // dev probe: cap the registers directly instead of through the launch bounds
 __global__ void __maxnreg__(RBIS_MAXNREG) rbis_fused_kernel(const __grid_constant__ KParams p) {
 #else
 __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constant__ KParams p) {
 #endif
-  static_assert(!(GENERAL && DC), "the DC variant has no general measurement path");
   extern __shared__ __align__(16) double smem[];
   __shared__ uint32_t tm_base_s;
   const int tid = threadIdx.x;
@@ -1491,17 +1496,12 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
           case 15: meas3<15, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           case 18: meas3<18, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
           default:
-            if (fast >= 100) {  // one-row chunk on state index fast - 100
-              meas1<DC>(P, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
-            } else if constexpr (GENERAL) {
-              double xs[NS];
-#pragma unroll
-              for (int c = 0; c < NS; c++) xs[c] = s.x[c];
-              const GenResult g = meas_general(st.chunk_len[ci], P, xs, st.has_orient, st.r_mode, st.m, st.idx,
-                                               st.z + op.row * st.m * st.cols, st.cols, sn, st.R, a0, N, n, dquat, chi0);
-#pragma unroll
-              for (int c = 0; c < NS; c++) s.x[c] += g.dx[c];
-              s.ll += g.dll;
+            if constexpr (BLOCKS) {
+              if (fast >= 100) {  // one-row chunk on state index fast - 100
+                meas1<DC>(P, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
+              } else {            // correlated rows: decorrelated scalar updates
+                meas_block<DC>(P, s, st, a0, st.chunk_len[ci], op.row, N, n, sn, dquat, chi0);
+              }
             }
             break;
         }

@@ -157,7 +157,7 @@ def test_scalar_updates_stay_on_the_decoupled_kernel_and_match_dense_and_oracle(
             b.set_state(sc["vec"], sc["quat"], sc["cov"])
             b.run_fused(ev, imu=st["imu"], streams=gs)
             out.append((b.get_state(), b.last_kernel_variant))
-    assert out[0][1] == DECOUPLED and out[1][1] == DENSE
+    assert out[0][1] == DECOUPLED + 1 and out[1][1] == DENSE + 1  # + 1: the instantiations with meas1 / meas_block
     _same(out[0][0], out[1][0])
     orc = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st) + extra, ev,
                               n_threads=NTHREADS)
