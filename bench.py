@@ -420,9 +420,9 @@ def run_b200(args):
     # bracket one launch's work: the K launches are timed as one region on the library's stream (b.record() makes that
     # stream join the internal group streams) and the mean launch duration is region / K.
     ev0, evk = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     gc.collect()
     gc.disable()
+    barrier()  # last thing before the clock starts: any skew between the ranks here is paid for in the final all-reduce
     t_wall0 = time.time()
     ev0.record(stream)
     for i in range(K):
