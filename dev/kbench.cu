@@ -15,6 +15,7 @@ struct Variant {
   const char* name;
   int tpb;
   int smem;
+  void (*geom)(long long N, int sms, int* grid, int* tpb, int* smem);
   void (*launch)(void* kparams_blob, int grid, int tpb, int smem, cudaStream_t st);
   size_t kparams_size;
   void (*fill)(void* blob, long long N, double* vec, double* quat, double* P, double* ll, double* q4, const double* imu,
@@ -63,6 +64,8 @@ int main(int argc, char** argv) {
   const char* only = argc > 3 ? argv[3] : nullptr;
   if (only && !strcmp(only, "-")) only = nullptr;
   const bool decoupled = argc > 4 ? atoi(argv[4]) != 0 : true;  // zero omega / a couplings in the initial covariance
+  const int schedule = argc > 5 ? atoi(argv[5]) : 3;            // 3: configs[2] (IMU + leg odometry + pose), 1: IMU only (configs[1])
+  const bool probes = argc > 6 ? atoi(argv[6]) != 0 : false;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s, %d SMs, N=%lld T=%d\n", prop.name, prop.multiProcessorCount, N, T);
@@ -70,7 +73,7 @@ int main(int argc, char** argv) {
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float ms;
   // ---- probes ----
-  {
+  if (probes) {
     double* d; CK(cudaMalloc(&d, 592 * 256 * 8 * 8));
     for (int lanes : {32, 16, 8}) {
       for (int wps : {4, 8, 16, 32}) {  // warps per SM (one block per SM)
@@ -99,13 +102,13 @@ int main(int argc, char** argv) {
   int li = 0, pi = 0;
   for (int k = 0; k < T; k++) {
     ops.push_back({0, 0, k, 1e-3});
-    if (k % 2 == 0) ops.push_back({1, 0, li++, 0});
-    if (k % 100 == 0) ops.push_back({1, 1, pi++, 0});
+    if (schedule == 3 && k % 2 == 0) ops.push_back({1, 0, li++, 0});
+    if (schedule == 3 && k % 100 == 0) ops.push_back({1, 1, pi++, 0});
   }
   srand(1);
   auto rnd = []() { return (rand() / (double)RAND_MAX) * 2 - 1; };
-  std::vector<double> vec(21 * N), quat(4 * N), P(231 * N), q4(4 * N), imu((size_t)T * 6 * N), z0((size_t)li * 3 * N),
-      z1((size_t)pi * 6 * N), q1((size_t)pi * 4 * N);
+  std::vector<double> vec(21 * N), quat(4 * N), P(231 * N), q4(4 * N), imu((size_t)T * 6 * N), z0((size_t)(li + 1) * 3 * N),
+      z1((size_t)(pi + 1) * 6 * N), q1((size_t)(pi + 1) * 4 * N);
   for (long long n = 0; n < N; n++) {
     for (int i = 0; i < 21; i++) vec[i * N + n] = 0.1 * rnd();
     vec[6 * N + n] = vec[7 * N + n] = vec[8 * N + n] = 0;
@@ -147,7 +150,9 @@ int main(int argc, char** argv) {
   for (auto& v : registry()) {
     if (only && !strstr(v.name, only)) continue;
     std::vector<char> blob(v.kparams_size, 0);
-    v.prep(v.smem);
+    int grid, tpb, smem;
+    v.geom(N, prop.multiProcessorCount, &grid, &tpb, &smem);
+    v.prep(smem);
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
       CK(cudaMemcpy(d_vec, vec.data(), vec.size() * 8, cudaMemcpyHostToDevice));
@@ -155,9 +160,8 @@ int main(int argc, char** argv) {
       CK(cudaMemcpy(d_P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
       CK(cudaMemset(d_ll, 0, N * 8));
       v.fill(blob.data(), N, d_vec, d_quat, d_P, d_ll, d_q4, d_imu, d_ops, (long long)ops.size(), d_z0, d_z1, d_q1, d_R0, d_R1);
-      int grid = (int)((N + v.tpb - 1) / v.tpb);
       CK(cudaEventRecord(e0));
-      v.launch(blob.data(), grid, v.tpb, v.smem, 0);
+      v.launch(blob.data(), grid, tpb, smem, 0);
       CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
       CK(cudaEventElapsedTime(&ms, e0, e1));
       if (ms < best) best = ms;
@@ -166,11 +170,11 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(out_P.data(), d_P, P.size() * 8, cudaMemcpyDeviceToHost));
     double ev = 0, eP = 0;
     if (ref_vec.empty()) { ref_vec = out_vec; ref_P = out_P; }
-    for (size_t i = 0; i < out_vec.size(); i++) ev = fmax(ev, fabs(out_vec[i] - ref_vec[i]));
+    for (size_t i = 0; i < out_vec.size(); i++) ev = fmax(ev, fabs(out_vec[i] - ref_vec[i]) / fmax(1.0, fabs(ref_vec[i])));
     for (size_t i = 0; i < out_P.size(); i++) eP = fmax(eP, fabs(out_P[i] - ref_P[i]) / 0.01);
     bool finite = true;
     for (size_t i = 0; i < out_vec.size(); i++) if (!std::isfinite(out_vec[i])) finite = false;
-    printf("%-28s %8.3f ms  %7.3f G filter-steps/s  (vs first: dvec %.2e dP %.2e finite=%d)\n", v.name, best,
+    printf("%-28s grid %4d x %3d thr, %6d B smem: %8.3f ms  %7.3f G filter-steps/s  (vs first: dvec %.2e dP %.2e finite=%d)\n", v.name, grid, tpb, smem, best,
            (double)N * T / (best * 1e-3) / 1e9, ev, eP, (int)finite);
   }
   return 0;

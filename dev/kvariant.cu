@@ -7,7 +7,15 @@
 #define KFUNC rbis_fused_kernel
 #define SET_FAST(s, c, v)
 #else
-#ifdef KDC
+#ifdef KGROUP
+#ifndef KDC
+#define KDC 0
+#endif
+#ifndef KMAXW
+#define KMAXW 8
+#endif
+#define KFUNC grp::rbis_group_kernel<KGROUP, (KDC != 0), KMAXW>
+#elif defined(KDC)
 #define KFUNC rbis_fused_kernel<false, true>
 #else
 #define KFUNC rbis_fused_kernel<false>
@@ -18,8 +26,12 @@
 #define KHEADER "../pronto_b200/csrc/rbis_kernels.cuh"
 #endif
 #include KHEADER
+#ifdef KGROUP
+#include "../pronto_b200/csrc/rbis_group.cuh"
+#endif
 struct Variant {
   const char* name; int tpb; int smem;
+  void (*geom)(long long, int, int*, int*, int*);
   void (*launch)(void*, int, int, int, cudaStream_t);
   size_t kparams_size;
   void (*fill)(void*, long long, double*, double*, double*, double*, double*, const double*, const void*, long long,
@@ -31,6 +43,30 @@ namespace {
 void launch(void* blob, int grid, int tpb, int smem, cudaStream_t st) {
   VNAME::KFUNC<<<grid, tpb, smem, st>>>(*(VNAME::KParams*)blob);
 }
+#ifdef KGROUP
+// warps per CTA so that the ensemble spreads over all SMs in whole waves
+void geom(long long N, int sms, int* grid, int* tpb, int* smem) {
+  using GE = VNAME::grp::Geo<KGROUP, (KDC != 0)>;
+  const long long warps = (N + GE::FPW - 1) / GE::FPW;
+  int maxw = KMAXW;
+  while (maxw > 1 && maxw * GE::FPW * GE::S * 8 > 232448) maxw--;
+#ifdef KWPC
+  int wpc = KWPC;
+#else
+  const long long waves = (warps + (long long)sms * maxw - 1) / ((long long)sms * maxw);
+  int wpc = (int)((warps + sms * waves - 1) / (sms * waves));
+#endif
+  if (wpc > maxw) wpc = maxw;
+  if (wpc < 1) wpc = 1;
+  *grid = (int)((warps + wpc - 1) / wpc);
+  *tpb = 32 * wpc;
+  *smem = wpc * GE::FPW * GE::S * 8;
+}
+#else
+void geom(long long N, int, int* grid, int* tpb, int* smem) {
+  *tpb = VNAME::TPB; *smem = VNAME::SMEM_BYTES; *grid = (int)((N + VNAME::TPB - 1) / VNAME::TPB);
+}
+#endif
 void prep(int smem) { cudaFuncSetAttribute(VNAME::KFUNC, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
 void fill(void* blob, long long N, double* vec, double* quat, double* P, double* ll, double* q4, const double* imu,
           const void* ops, long long n_ops, const double* z0, const double* z1, const double* q1, const double* R0,
@@ -50,5 +86,5 @@ void fill(void* blob, long long N, double* vec, double* quat, double* P, double*
   s1.chunk_start[0] = 0; s1.chunk_len[0] = 3; s1.chunk_start[1] = 3; s1.chunk_len[1] = 3; SET_FAST(s1, 0, 9); SET_FAST(s1, 1, 6); s1.z = z1; s1.quat = q1; s1.R = R1; s1.cols = N;
   std::memcpy(blob, &kp, sizeof(kp));
 }
-struct Reg { Reg() { registry().push_back({VTAG, VNAME::TPB, VNAME::SMEM_BYTES, launch, sizeof(VNAME::KParams), fill, prep}); } } reg;
+struct Reg { Reg() { registry().push_back({VTAG, VNAME::TPB, VNAME::SMEM_BYTES, geom, launch, sizeof(VNAME::KParams), fill, prep}); } } reg;
 }  // namespace

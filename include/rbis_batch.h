@@ -87,6 +87,13 @@ typedef struct {
                               until a measurement indexes omega or a -- and no stream of the program indexes omega or a;
                               results are bit-identical to the dense variant.
                               1 = always run the dense variant (whole covariance on chip, 256 filters per SM). */
+  int32_t mapping;         /* lanes that cooperate on one filter in the fused kernels.  1 = the lane-per-filter kernels (a
+                              B200 needs ~57,000 filters to fill them); 2, 4, 8, 16 = the warp-group kernels for small or
+                              split ensembles (BASELINE configs[1], a 65,536-filter ensemble sharded over 8 GPUs): the
+                              covariance products of MSE/rbis.cpp:113-118,134-140 are split over the lanes of a group, the
+                              covariance is carried as a full unsymmetrised matrix inside a launch as in the reference.
+                              0 (default) = automatic by ensemble size.  Results of the two mappings agree to rounding
+                              (a few ulp per step; tests/test_gpu_group.py), not bit for bit. */
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /
@@ -130,7 +137,8 @@ void* rbis_batch_stream(rbis_batch_t* h);
 int64_t rbis_batch_launch_count(const rbis_batch_t* h);
 /* Kernel variant the last rbis_batch_run_fused / single-op call launched: 0 dense, 2 decoupled (see
  * rbis_batch_config_t::dense_only), +1 when the program has measurement chunks other than uncorrelated aligned index
- * triples (the instantiations that also contain the one-row and the correlated-block updates); -1 before the first launch. */
+ * triples (the instantiations that also contain the one-row and the correlated-block updates), + 16 * lanes per filter
+ * for the warp-group kernels (rbis_batch_config_t::mapping > 1); -1 before the first launch. */
 int rbis_batch_last_kernel_variant(const rbis_batch_t* h);
 
 /* ---- RBISResetUpdate::updateFilter (MSE/rbis_update_interface.cpp:23-28): posterior := given,

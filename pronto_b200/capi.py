@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("launch_groups", C.c_int32),
         ("dense_only", C.c_int32),
+        ("mapping", C.c_int32),
     ]
 
 

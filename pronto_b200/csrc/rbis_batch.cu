@@ -13,6 +13,7 @@
 
 #include "../../include/rbis_batch.h"
 #include "rbis_kernels.cuh"   // namespace rbisk: 256 filters per CTA, whole covariance on chip (any filter, any program)
+#include "rbis_group.cuh"     // namespace rbisk::grp: the warp-group mapping (G lanes per filter) for small ensembles
 // Second configuration of the same device code, namespace rbisk_dc: 384 filters per CTA, only the 15x15 active block
 // on chip -- the DC ("decoupled") kernels for ensembles whose omega / a couplings are exactly zero (rbis_kernels.cuh).
 #define rbisk rbisk_dc
@@ -118,7 +119,10 @@ struct rbis_batch {
   double* d_notch_state = nullptr;  // [3][MAX_NOTCH][4][notch_cols]
   int64_t notch_cols = 0;
   DevBuf notch_stage;               // device copy of a host chunk
-  int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block
+  int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block, bits 4.. lanes per filter (0 = one)
+  int mapping = 1;        // lanes per filter of the fused kernels: 1 = lane-per-filter kernels, 2/4/8/16 = warp-group kernels
+  int n_sms = 148;
+  long long last_part = -1;  // filters per launch-group range of the last grouped launch (ranges differ between kernel variants)
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
   DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
@@ -161,17 +165,86 @@ constexpr int kSmemBytes = rbisk::SMEM_BYTES;
 constexpr int kRShared = rbisk::RS_STRIDE;
 constexpr int kSmemBytesDc = rbisk_dc::SMEM_BYTES;
 
-// variant: bit 1 = decoupled, bit 0 = the program has measurement chunks other than aligned triples (meas1 / meas_block compiled in)
-void launch_variant(int variant, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
+// ---- warp-group kernels (rbis_group.cuh): one instantiation per (lanes per filter, decoupled) ----
+struct GroupKernel {
+  int G, dc, maxw, fpw, stride;  // lanes per filter, decoupled, max warps per CTA, filters per warp, doubles of shared memory per filter
+  const void* fn;
+};
+constexpr int kGroupMaxW = 8;
+template <int G, bool DC>
+GroupKernel group_kernel() {
+  using GE = rbisk::grp::Geo<G, DC>;
+  return {G, DC ? 1 : 0, kGroupMaxW, GE::FPW, GE::S, (const void*)rbisk::grp::rbis_group_kernel<G, DC, kGroupMaxW>};
+}
+const GroupKernel* group_kernels(int* n) {
+  static const GroupKernel k[] = {group_kernel<2, true>(),  group_kernel<4, true>(),  group_kernel<8, true>(),  group_kernel<16, true>(),
+                                  group_kernel<2, false>(), group_kernel<4, false>(), group_kernel<8, false>(), group_kernel<16, false>()};
+  *n = (int)(sizeof(k) / sizeof(k[0]));
+  return k;
+}
+const GroupKernel* find_group_kernel(int G, bool dc) {
+  int n;
+  const GroupKernel* k = group_kernels(&n);
+  for (int i = 0; i < n; i++)
+    if (k[i].G == G && k[i].dc == (dc ? 1 : 0)) return &k[i];
+  return nullptr;
+}
+constexpr int kMaxSmemOptin = 232448;
+
+// Launch geometry of a fused launch.  variant: bit 1 = decoupled, bit 0 = the program has measurement chunks other than
+// aligned triples (lane-per-filter kernels only: the instantiations with meas1 / meas_block); mapping = lanes per filter.
+struct LaunchGeom {
+  unsigned grid;        // CTAs for the whole ensemble
+  int threads, smem;
+  long long fpc;        // filters per CTA
+};
+LaunchGeom launch_geom(int variant, int mapping, long long N, int n_sms) {
+  LaunchGeom g{};
+  if (mapping <= 1) {
+    g.threads = (variant & 2) ? rbisk_dc::TPB : rbisk::TPB;
+    g.smem = (variant & 2) ? rbisk_dc::SMEM_BYTES : rbisk::SMEM_BYTES;
+    g.fpc = g.threads;
+  } else {
+    // warps per CTA so that the ensemble spreads over all SMs in whole waves
+    const GroupKernel* k = find_group_kernel(mapping, (variant & 2) != 0);
+    int maxw = k->maxw;
+    while (maxw > 1 && (long long)maxw * k->fpw * k->stride * 8 > kMaxSmemOptin) maxw--;
+    const long long warps = (N + k->fpw - 1) / k->fpw;
+    const long long waves = (warps + (long long)n_sms * maxw - 1) / ((long long)n_sms * maxw);
+    long long wpc = (warps + n_sms * waves - 1) / (n_sms * waves);
+    if (wpc > maxw) wpc = maxw;
+    if (wpc < 1) wpc = 1;
+    g.threads = 32 * (int)wpc;
+    g.smem = (int)(wpc * k->fpw * k->stride * 8);
+    g.fpc = wpc * k->fpw;
+  }
+  g.grid = (unsigned)((N + g.fpc - 1) / g.fpc);
+  return g;
+}
+
+cudaError_t launch_variant(int variant, int mapping, const LaunchGeom& g, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
+  if (mapping > 1) {
+    const GroupKernel* k = find_group_kernel(mapping, (variant & 2) != 0);
+    void* args[] = {(void*)&kp};
+    return cudaLaunchKernel(k->fn, dim3(blocks), dim3((unsigned)g.threads), args, (size_t)g.smem, st);
+  }
   if (variant & 2) {
     rbisk_dc::KParams kd;
     std::memcpy(&kd, &kp, sizeof(kd));
-    if (variant & 1) rbisk_dc::rbis_fused_kernel<true, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
-    else rbisk_dc::rbis_fused_kernel<false, true><<<blocks, rbisk_dc::TPB, kSmemBytesDc, st>>>(kd);
+    if (variant & 1) rbisk_dc::rbis_fused_kernel<true, true><<<blocks, g.threads, g.smem, st>>>(kd);
+    else rbisk_dc::rbis_fused_kernel<false, true><<<blocks, g.threads, g.smem, st>>>(kd);
   } else {
-    if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
-    else rbisk::rbis_fused_kernel<false><<<blocks, rbisk::TPB, kSmemBytes, st>>>(kp);
+    if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, g.threads, g.smem, st>>>(kp);
+    else rbisk::rbis_fused_kernel<false><<<blocks, g.threads, g.smem, st>>>(kp);
   }
+  return cudaGetLastError();
+}
+
+// Lanes per filter when rbis_batch_config_t::mapping is 0 (automatic): measured on a B200 (dev/kbench).
+int auto_mapping(long long N) {
+  if (N > 12288) return 1;
+  if (N > 2048) return 4;
+  return 8;
 }
 
 int use_device(const rbis_batch* h) {
@@ -436,8 +509,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     h->decoupled = flag ? 0 : 1;
   }
   if (dc_eligible && h->decoupled == 1) variant |= 2;
-  const int tpb = (variant & 2) ? rbisk_dc::TPB : rbisk::TPB;
-  const unsigned grid = (unsigned)((N + tpb - 1) / tpb);
+  const LaunchGeom geom = launch_geom(variant, h->mapping, N, h->n_sms);
+  const unsigned grid = geom.grid;
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
     if (staging) CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
@@ -459,8 +532,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     kp.ops = h->d_ops;
     kp.block_offset = 0;
-    launch_variant(variant, grid, h->stream, kp);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_variant(variant, h->mapping, geom, grid, h->stream, kp));
     h->launches++;
     if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
   } else {
@@ -482,22 +554,29 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     const bool wait_main = h->stream_dirty;
     if (wait_main) CUDA_TRY(cudaEventRecord(h->pre_evt, h->stream));
     const unsigned per = (grid + (unsigned)h->n_groups - 1) / (unsigned)h->n_groups;
+    // Group g of this launch may only run ahead of the other groups of the previous launch when both launches cut the
+    // ensemble into the SAME filter ranges.  The ranges are per * (filters per CTA), and the filters per CTA differ between
+    // kernel variants (256 dense, 384 decoupled, ...): after a change every group waits for ALL groups of the previous launch.
+    const long long part = (long long)per * geom.fpc;
+    const bool repartitioned = h->last_ring >= 0 && h->groups_dirty && h->last_part != part;
     for (int g = 0; g < h->n_groups; g++) {
       const unsigned b0 = (unsigned)g * per, b1 = b0 + per < grid ? b0 + per : grid;
       cudaStream_t gs = h->gstream[g];
+      if (repartitioned)
+        for (int g2 = 0; g2 < h->n_groups; g2++) CUDA_TRY(cudaStreamWaitEvent(gs, h->gdone[h->last_ring][g2], 0));
       if (wait_main) CUDA_TRY(cudaStreamWaitEvent(gs, h->pre_evt, 0));
       if (staging) CUDA_TRY(cudaStreamWaitEvent(gs, slot.copied, 0));
       CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
       if (b1 > b0) {
         kp.block_offset = (int)b0;
-        launch_variant(variant, b1 - b0, gs, kp);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_variant(variant, h->mapping, geom, b1 - b0, gs, kp));
         h->launches++;
       }
       CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
     }
     h->gdone_valid[ring] = true;
     h->last_ring = ring;
+    h->last_part = part;
     h->groups_dirty = true;
     h->stream_dirty = false;
     if (staging) slot.ring = ring;
@@ -517,7 +596,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       if (f == 2) f = as_launch;
   }
   h->snap_dc = snap_dc;
-  h->last_variant = variant;
+  h->last_variant = variant | (h->mapping > 1 ? (h->mapping << 4) : 0);
   h->utime = last_utime;
   return 0;
 }
@@ -538,6 +617,7 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->device = 0;
   cfg->launch_groups = 0;
   cfg->dense_only = 0;
+  cfg->mapping = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -549,6 +629,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   if (c.snapshot_slots < 0) return fail(RBIS_ERR_INVALID, "snapshot_slots must be >= 0");
   if (c.launch_groups < 0 || c.launch_groups > rbis_batch::kMaxGroups)
     return fail(RBIS_ERR_INVALID, "launch_groups must be in [0, %d]", rbis_batch::kMaxGroups);
+  if (c.mapping != 0 && c.mapping != 1 && c.mapping != 2 && c.mapping != 4 && c.mapping != 8 && c.mapping != 16)
+    return fail(RBIS_ERR_INVALID, "mapping must be 0 (automatic), 1, 2, 4, 8 or 16 lanes per filter");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -569,6 +651,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   h->N = n_filters;
   h->cfg = c;
   h->smem_bytes = kSmemBytes;
+  h->n_sms = prop.multiProcessorCount;
+  h->mapping = c.mapping ? c.mapping : auto_mapping(n_filters);
   const size_t N = (size_t)n_filters;
   auto cleanup = [&](int code) { rbis_batch_destroy(h); return code; };
 #define CREATE_TRY(expr)                                                                             \
@@ -587,7 +671,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     const long long ctas = (long long)((n_filters + rbisk::TPB - 1) / rbisk::TPB), sms = prop.multiProcessorCount;
     const long long ctas_dc = (long long)((n_filters + rbisk_dc::TPB - 1) / rbisk_dc::TPB);
     int g = c.launch_groups;
-    if (g == 0) g = ((ctas > sms && ctas % sms != 0) || (!c.dense_only && ctas_dc > sms && ctas_dc % sms != 0)) ? 6 : 1;
+    if (g == 0) g = (h->mapping == 1 && ((ctas > sms && ctas % sms != 0) || (!c.dense_only && ctas_dc > sms && ctas_dc % sms != 0))) ? 6 : 1;
     if ((long long)g > ctas_dc) g = (int)ctas_dc;
     if ((long long)g > ctas) g = (int)ctas;
     h->n_groups = g < 1 ? 1 : g;
@@ -624,6 +708,11 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  {
+    int nk;
+    const GroupKernel* gk = group_kernels(&nk);
+    for (int i = 0; i < nk; i++) CREATE_TRY(cudaFuncSetAttribute(gk[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  }
   // default state: zeros, identity quaternion, zero covariance, zero process noise
   CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
   CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));
