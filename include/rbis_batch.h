@@ -91,9 +91,13 @@ typedef struct {
                               B200 needs ~57,000 filters to fill them); 2, 4, 8, 16 = the warp-group kernels for small or
                               split ensembles (BASELINE configs[1], a 65,536-filter ensemble sharded over 8 GPUs): the
                               covariance products of MSE/rbis.cpp:113-118,134-140 are split over the lanes of a group, the
-                              covariance is carried as a full unsymmetrised matrix inside a launch as in the reference.
-                              0 (default) = automatic by ensemble size.  Results of the two mappings agree to rounding
-                              (a few ulp per step; tests/test_gpu_group.py), not bit for bit. */
+                              covariance is carried as a full matrix in shared memory.
+                              0 (default) = automatic by ensemble size.  Results of the two mappings agree
+                              BIT FOR BIT (every covariance element is computed by the same expression in both;
+                              tests/test_gpu_group.py), so the choice is invisible in the results. */
+  int32_t lane_filters_per_cta; /* filters per CTA of the decoupled lane-per-filter kernels: 384 (three warps per scheduler, for
+                              ensembles that fill the GPU), 256 or 128 (more SMs busy for 10-50 thousand filters); 0 = automatic.
+                              Same bits for every value. */
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /

@@ -35,6 +35,7 @@ class Config(C.Structure):
         ("launch_groups", C.c_int32),
         ("dense_only", C.c_int32),
         ("mapping", C.c_int32),
+        ("lane_filters_per_cta", C.c_int32),
     ]
 
 

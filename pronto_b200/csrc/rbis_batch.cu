@@ -12,27 +12,12 @@
 #include <vector>
 
 #include "../../include/rbis_batch.h"
-#include "rbis_kernels.cuh"   // namespace rbisk: 256 filters per CTA, whole covariance on chip (any filter, any program)
-#include "rbis_group.cuh"     // namespace rbisk::grp: the warp-group mapping (G lanes per filter) for small ensembles
-// Second configuration of the same device code, namespace rbisk_dc: 384 filters per CTA, only the 15x15 active block
-// on chip -- the DC ("decoupled") kernels for ensembles whose omega / a couplings are exactly zero (rbis_kernels.cuh).
-#define rbisk rbisk_dc
-#define RBIS_FUSED_ONLY 1
-#undef RBIS_TPB
-#define RBIS_TPB 384
-#undef RBIS_PLACEMENT
-#define RBIS_PLACEMENT 2
-#undef RBIS_LATE_LOADS
-#define RBIS_LATE_LOADS 1
-#undef RBIS_PARK_STATE
-#define RBIS_PARK_STATE 2   // 168 registers per thread: the filter state waits in spare tensor memory during a measurement sweep
-#undef RBIS_PARK_COV_KEEP
-#define RBIS_PARK_COV_KEEP 0x3ffffffu  // ... and stays in registers during the covariance step (no spills either way, fewer TMEM ops)
-#include "rbis_kernels.cuh"
-#undef rbisk
+#include "rbis_kernels.cuh"   // namespace rbisk: the DENSE lane-per-filter kernels (256 filters per CTA, whole covariance on chip)
 #include "rbis_stats.cuh"
 #include "rbis_smooth.cuh"
-static_assert(sizeof(rbisk::KParams) == sizeof(rbisk_dc::KParams), "both kernel configurations take the same parameter block");
+// The other fused-kernel configurations live in translation units of their own (rbis_fused_*.cu over rbis_fused_tu.inc):
+// the decoupled lane-per-filter kernels at 384 / 256 / 128 filters per CTA and the warp-group kernels of rbis_group.cuh.
+#include "rbis_fused_tu.h"
 
 namespace {
 
@@ -121,6 +106,7 @@ struct rbis_batch {
   DevBuf notch_stage;               // device copy of a host chunk
   int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block, bits 4.. lanes per filter (0 = one)
   int mapping = 1;        // lanes per filter of the fused kernels: 1 = lane-per-filter kernels, 2/4/8/16 = warp-group kernels
+  int lane_tpb = 384;     // filters per CTA of the decoupled lane-per-filter kernels (384, 256, 128)
   int n_sms = 148;
   long long last_part = -1;  // filters per launch-group range of the last grouped launch (ranges differ between kernel variants)
   DevBuf full_cov;      // [441][N] scratch for set/get_state
@@ -163,88 +149,107 @@ constexpr int kSmemBytes = rbisk::SMEM_BYTES;
 // per stream in the shared-R device buffer: R (m x m column-major, 81), then for its correlated blocks the rows of
 // L_R^-1 ([9][9] row-major, absolute row numbers) and D_R ([9]) of R_block = L_R D_R L_R^T (rbisk::RS_W, RS_D)
 constexpr int kRShared = rbisk::RS_STRIDE;
-constexpr int kSmemBytesDc = rbisk_dc::SMEM_BYTES;
 
-// ---- warp-group kernels (rbis_group.cuh): one instantiation per (lanes per filter, decoupled) ----
-struct GroupKernel {
-  int G, dc, maxw, fpw, stride;  // lanes per filter, decoupled, max warps per CTA, filters per warp, doubles of shared memory per filter
-  const void* fn;
-};
-constexpr int kGroupMaxW = 8;
-template <int G, bool DC>
-GroupKernel group_kernel() {
-  using GE = rbisk::grp::Geo<G, DC>;
-  return {G, DC ? 1 : 0, kGroupMaxW, GE::FPW, GE::S, (const void*)rbisk::grp::rbis_group_kernel<G, DC, kGroupMaxW>};
-}
-const GroupKernel* group_kernels(int* n) {
-  static const GroupKernel k[] = {group_kernel<2, true>(),  group_kernel<4, true>(),  group_kernel<8, true>(),  group_kernel<16, true>(),
-                                  group_kernel<2, false>(), group_kernel<4, false>(), group_kernel<8, false>(), group_kernel<16, false>()};
-  *n = (int)(sizeof(k) / sizeof(k[0]));
-  return k;
-}
-const GroupKernel* find_group_kernel(int G, bool dc) {
-  int n;
-  const GroupKernel* k = group_kernels(&n);
-  for (int i = 0; i < n; i++)
-    if (k[i].G == G && k[i].dc == (dc ? 1 : 0)) return &k[i];
+constexpr int kMaxSmemOptin = 232448;
+const rbis_fused_tu_t* const kLaneTus[] = {&rbis_fused_tu_dc384, &rbis_fused_tu_dc256, &rbis_fused_tu_dc128};
+const rbis_fused_tu_t* const kGroupTus[] = {&rbis_fused_tu_g2, &rbis_fused_tu_g4, &rbis_fused_tu_g8, &rbis_fused_tu_g16};
+const rbis_fused_tu_t* group_tu(int G) {
+  for (const rbis_fused_tu_t* t : kGroupTus)
+    if (t->lanes_per_filter == G) return t;
   return nullptr;
 }
-constexpr int kMaxSmemOptin = 232448;
+const rbis_fused_tu_t* lane_tu(int tpb) {
+  for (const rbis_fused_tu_t* t : kLaneTus)
+    if (t->threads == tpb) return t;
+  return nullptr;
+}
 
 // Launch geometry of a fused launch.  variant: bit 1 = decoupled, bit 0 = the program has measurement chunks other than
-// aligned triples (lane-per-filter kernels only: the instantiations with meas1 / meas_block); mapping = lanes per filter.
+// aligned triples (lane-per-filter kernels only: the instantiations with meas1 / meas_block); mapping = lanes per filter;
+// lane_tpb = filters per CTA of the decoupled lane-per-filter kernels (384, 256 or 128; the dense ones are 256).
 struct LaunchGeom {
   unsigned grid;        // CTAs for the whole ensemble
   int threads, smem;
   long long fpc;        // filters per CTA
+  const rbis_fused_tu_t* tu;  // nullptr: the dense lane-per-filter kernels of this translation unit
 };
-LaunchGeom launch_geom(int variant, int mapping, long long N, int n_sms) {
+LaunchGeom launch_geom(int variant, int mapping, int lane_tpb, long long N, int n_sms) {
   LaunchGeom g{};
   if (mapping <= 1) {
-    g.threads = (variant & 2) ? rbisk_dc::TPB : rbisk::TPB;
-    g.smem = (variant & 2) ? rbisk_dc::SMEM_BYTES : rbisk::SMEM_BYTES;
+    g.tu = (variant & 2) ? lane_tu(lane_tpb) : nullptr;
+    g.threads = g.tu ? g.tu->threads : rbisk::TPB;
+    g.smem = g.tu ? g.tu->smem : rbisk::SMEM_BYTES;
     g.fpc = g.threads;
   } else {
     // warps per CTA so that the ensemble spreads over all SMs in whole waves
-    const GroupKernel* k = find_group_kernel(mapping, (variant & 2) != 0);
-    int maxw = k->maxw;
-    while (maxw > 1 && (long long)maxw * k->fpw * k->stride * 8 > kMaxSmemOptin) maxw--;
-    const long long warps = (N + k->fpw - 1) / k->fpw;
+    g.tu = group_tu(mapping);
+    const int stride = (variant & 2) ? (g.tu->smem_doubles_per_filter & 0xffff) : (g.tu->smem_doubles_per_filter >> 16);
+    const int fpw = g.tu->filters_per_warp;
+    int maxw = g.tu->max_warps;
+    while (maxw > 1 && (long long)maxw * fpw * stride * 8 > kMaxSmemOptin) maxw--;
+    const long long warps = (N + fpw - 1) / fpw;
     const long long waves = (warps + (long long)n_sms * maxw - 1) / ((long long)n_sms * maxw);
     long long wpc = (warps + n_sms * waves - 1) / (n_sms * waves);
     if (wpc > maxw) wpc = maxw;
     if (wpc < 1) wpc = 1;
     g.threads = 32 * (int)wpc;
-    g.smem = (int)(wpc * k->fpw * k->stride * 8);
-    g.fpc = wpc * k->fpw;
+    g.smem = (int)(wpc * fpw * stride * 8);
+    g.fpc = wpc * fpw;
   }
   g.grid = (unsigned)((N + g.fpc - 1) / g.fpc);
   return g;
 }
 
-cudaError_t launch_variant(int variant, int mapping, const LaunchGeom& g, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
-  if (mapping > 1) {
-    const GroupKernel* k = find_group_kernel(mapping, (variant & 2) != 0);
-    void* args[] = {(void*)&kp};
-    return cudaLaunchKernel(k->fn, dim3(blocks), dim3((unsigned)g.threads), args, (size_t)g.smem, st);
-  }
-  if (variant & 2) {
-    rbisk_dc::KParams kd;
-    std::memcpy(&kd, &kp, sizeof(kd));
-    if (variant & 1) rbisk_dc::rbis_fused_kernel<true, true><<<blocks, g.threads, g.smem, st>>>(kd);
-    else rbisk_dc::rbis_fused_kernel<false, true><<<blocks, g.threads, g.smem, st>>>(kd);
-  } else {
-    if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, g.threads, g.smem, st>>>(kp);
-    else rbisk::rbis_fused_kernel<false><<<blocks, g.threads, g.smem, st>>>(kp);
-  }
+cudaError_t launch_variant(int variant, const LaunchGeom& g, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
+  if (g.tu) return g.tu->launch(variant & 1, (variant & 2) ? 1 : 0, blocks, g.threads, g.smem, st, &kp);
+  if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, g.threads, g.smem, st>>>(kp);
+  else rbisk::rbis_fused_kernel<false><<<blocks, g.threads, g.smem, st>>>(kp);
   return cudaGetLastError();
 }
 
-// Lanes per filter when rbis_batch_config_t::mapping is 0 (automatic): measured on a B200 (dev/kbench).
-int auto_mapping(long long N) {
-  if (N > 12288) return 1;
-  if (N > 2048) return 4;
-  return 8;
+// Automatic choice of the mapping (rbis_batch_config_t::mapping == 0) from the ensemble size: cycles per filter step of one
+// wave of CTAs, measured on a B200 with dev/kbench (config-3 program, decoupled kernels), times the number
+// of waves.  All candidates compute the same bits, so this is a pure scheduling decision.
+struct MappingChoice {
+  int mapping, lane_tpb;
+};
+int auto_mapping_lane_only(long long N, int n_sms);
+MappingChoice auto_mapping(long long N, int n_sms) {
+  struct Cand { int mapping, tpb; double cycles; };
+  double best = 1e300;
+  MappingChoice pick{1, 384};
+  auto consider = [&](int mapping, int tpb, double cost) {
+    if (cost < best) { best = cost; pick = {mapping, tpb}; }
+  };
+  auto waves = [&](long long ctas) { return (double)((ctas + n_sms - 1) / n_sms); };
+  // lane-per-filter: one CTA per SM; large ensembles overlap their waves through the launch groups, so beyond one wave
+  // the cost grows with the CTA count, not with whole waves
+  const struct { int tpb; double cyc; } lane[] = {{384, 16200.0}, {256, 12500.0}, {128, 9300.0}};
+  for (const auto& k : lane) {
+    const long long ctas = (N + k.tpb - 1) / k.tpb;
+    const double w = ctas <= n_sms ? 1.0 : (k.tpb == 384 ? (double)ctas / n_sms : waves(ctas));
+    consider(1, k.tpb, w * k.cyc);
+  }
+  // warp groups of 4 lanes: one wave holds n_sms * 8 warps * 8 filters; cost grows with the warps per CTA
+  {
+    const long long warps = (N + 7) / 8;
+    const long long wv = (warps + (long long)n_sms * 8 - 1) / ((long long)n_sms * 8);
+    const double wpc = (double)((warps + n_sms * wv - 1) / (n_sms * wv));
+    consider(4, 384, (double)wv * (4300.0 + 560.0 * wpc));
+  }
+  return pick;
+}
+
+int auto_mapping_lane_only(long long N, int n_sms) {
+  const struct { int tpb; double cyc; } lane[] = {{384, 16200.0}, {256, 12500.0}, {128, 9300.0}};
+  double best = 1e300;
+  int pick = 384;
+  for (const auto& k : lane) {
+    const long long ctas = (N + k.tpb - 1) / k.tpb;
+    const double w = ctas <= n_sms ? 1.0 : (k.tpb == 384 ? (double)ctas / n_sms : (double)((ctas + n_sms - 1) / n_sms));
+    if (w * k.cyc < best) { best = w * k.cyc; pick = k.tpb; }
+  }
+  return pick;
 }
 
 int use_device(const rbis_batch* h) {
@@ -509,7 +514,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     h->decoupled = flag ? 0 : 1;
   }
   if (dc_eligible && h->decoupled == 1) variant |= 2;
-  const LaunchGeom geom = launch_geom(variant, h->mapping, N, h->n_sms);
+  const LaunchGeom geom = launch_geom(variant, h->mapping, h->lane_tpb, N, h->n_sms);
   const unsigned grid = geom.grid;
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
@@ -532,7 +537,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     kp.ops = h->d_ops;
     kp.block_offset = 0;
-    CUDA_TRY(launch_variant(variant, h->mapping, geom, grid, h->stream, kp));
+    CUDA_TRY(launch_variant(variant, geom, grid, h->stream, kp));
     h->launches++;
     if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
   } else {
@@ -569,7 +574,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
       if (b1 > b0) {
         kp.block_offset = (int)b0;
-        CUDA_TRY(launch_variant(variant, h->mapping, geom, b1 - b0, gs, kp));
+        CUDA_TRY(launch_variant(variant, geom, b1 - b0, gs, kp));
         h->launches++;
       }
       CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
@@ -618,6 +623,7 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->launch_groups = 0;
   cfg->dense_only = 0;
   cfg->mapping = 0;
+  cfg->lane_filters_per_cta = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -631,6 +637,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     return fail(RBIS_ERR_INVALID, "launch_groups must be in [0, %d]", rbis_batch::kMaxGroups);
   if (c.mapping != 0 && c.mapping != 1 && c.mapping != 2 && c.mapping != 4 && c.mapping != 8 && c.mapping != 16)
     return fail(RBIS_ERR_INVALID, "mapping must be 0 (automatic), 1, 2, 4, 8 or 16 lanes per filter");
+  if (c.lane_filters_per_cta != 0 && c.lane_filters_per_cta != 384 && c.lane_filters_per_cta != 256 && c.lane_filters_per_cta != 128)
+    return fail(RBIS_ERR_INVALID, "lane_filters_per_cta must be 0 (automatic), 384, 256 or 128");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -652,7 +660,15 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   h->cfg = c;
   h->smem_bytes = kSmemBytes;
   h->n_sms = prop.multiProcessorCount;
-  h->mapping = c.mapping ? c.mapping : auto_mapping(n_filters);
+  {
+    const MappingChoice mc = auto_mapping(n_filters, h->n_sms);
+    h->mapping = c.mapping ? c.mapping : mc.mapping;
+    h->lane_tpb = c.lane_filters_per_cta ? c.lane_filters_per_cta : (c.mapping == 1 ? auto_mapping_lane_only(n_filters, h->n_sms) : mc.lane_tpb);
+    for (const rbis_fused_tu_t* t : kLaneTus)
+      if (t->kparams_bytes != sizeof(rbisk::KParams)) { fail(RBIS_ERR_CUDA, "kernel parameter block mismatch between translation units"); rbis_batch_destroy(h); return RBIS_ERR_CUDA; }
+    for (const rbis_fused_tu_t* t : kGroupTus)
+      if (t->kparams_bytes != sizeof(rbisk::KParams)) { fail(RBIS_ERR_CUDA, "kernel parameter block mismatch between translation units"); rbis_batch_destroy(h); return RBIS_ERR_CUDA; }
+  }
   const size_t N = (size_t)n_filters;
   auto cleanup = [&](int code) { rbis_batch_destroy(h); return code; };
 #define CREATE_TRY(expr)                                                                             \
@@ -669,7 +685,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   {
     // launch groups: explicit, or automatic = 6 when the CTAs do not fill a whole number of waves (measured: 2 groups 2.12, 3: 1.92, 4: 1.89, 6: 1.865, 8: 1.88 ms per launch)
     const long long ctas = (long long)((n_filters + rbisk::TPB - 1) / rbisk::TPB), sms = prop.multiProcessorCount;
-    const long long ctas_dc = (long long)((n_filters + rbisk_dc::TPB - 1) / rbisk_dc::TPB);
+    const long long ctas_dc = (long long)((n_filters + h->lane_tpb - 1) / h->lane_tpb);
     int g = c.launch_groups;
     if (g == 0) g = (h->mapping == 1 && ((ctas > sms && ctas % sms != 0) || (!c.dense_only && ctas_dc > sms && ctas_dc % sms != 0))) ? 6 : 1;
     if ((long long)g > ctas_dc) g = (int)ctas_dc;
@@ -704,15 +720,10 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   }
   CREATE_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rbisk::SMOOTH_SMEM_BYTES));
-  CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
-  CREATE_TRY(cudaFuncSetAttribute(rbisk_dc::rbis_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesDc));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  {
-    int nk;
-    const GroupKernel* gk = group_kernels(&nk);
-    for (int i = 0; i < nk; i++) CREATE_TRY(cudaFuncSetAttribute(gk[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-  }
+  for (const rbis_fused_tu_t* t : kLaneTus) CREATE_TRY(t->prepare());
+  for (const rbis_fused_tu_t* t : kGroupTus) CREATE_TRY(t->prepare());
   // default state: zeros, identity quaternion, zero covariance, zero process noise
   CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
   CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));

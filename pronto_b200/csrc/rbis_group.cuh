@@ -28,6 +28,9 @@
 // Included by rbis_batch.cu after the first (default-configuration) inclusion of rbis_kernels.cuh.
 #ifndef RBIS_GROUP_CUH_
 #define RBIS_GROUP_CUH_
+#ifndef RBIS_GROUP_STATE_FIRST
+#define RBIS_GROUP_STATE_FIRST 0  // insUpdateState before (1) or after (0) the covariance passes of an IMU step (dev knob; 0 measured 5-10 % faster)
+#endif
 
 namespace rbisk {
 namespace grp {
@@ -380,6 +383,10 @@ __device__ __forceinline__ void g_meas3(double* Pf, const int l, FilterState& s,
   }
   g_sweep<G, DC, 3>(Pf, w, Y, wj);
   __syncwarp();
+#ifdef RBIS_GROUP_COVONLY
+  s.ll += logdet + z[0] + z[1] + z[2] + Y[0][3] + Y[1][7] + Y[2][11];
+  return;
+#endif
   double r[3];
   if (I0 == 6 && st.has_orient) {
     r[0] = dquat.x - (s.x[6] - chi0.x); r[1] = dquat.y - (s.x[7] - chi0.y); r[2] = dquat.z - (s.x[8] - chi0.z);
@@ -590,10 +597,33 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
   qn.q_gyro = __ldg(p.q_gyro + n); qn.q_accel = __ldg(p.q_accel + n);
   qn.q_gyro_bias = __ldg(p.q_gyro_bias + n); qn.q_accel_bias = __ldg(p.q_accel_bias + n);
 
-  Op op_next = load_op(0);
+  // Ops are fetched two ahead, and the INPUT ROWS of the next op are prefetched into L1 while the current op runs: with
+  // one or two warps per scheduler nothing else hides the latency of a first touch of HBM.
+  auto prefetch = [&](const double* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
+  auto prefetch_inputs = [&](const Op& o) {
+    if (o.kind == 0) {
+      const double* base = p.imu + o.row * 6 * p.imu_cols + imu_n;
+#pragma unroll
+      for (int k = 0; k < 6; k++) prefetch(base + k * p.imu_cols);
+    } else if (o.kind == 1) {
+      const StreamDesc& st = p.streams[o.stream];
+      const long long sn = st.map ? (long long)__ldg(st.map + n) : n;
+      const double* zb = st.z + o.row * st.m * st.cols + sn;
+      for (int a = 0; a < st.m; a++) prefetch(zb + a * st.cols);
+      if (st.has_orient) {
+        const double* qb = st.quat + o.row * 4 * st.cols + sn;
+#pragma unroll
+        for (int k = 0; k < 4; k++) prefetch(qb + k * st.cols);
+      }
+    }
+  };
+  Op op1 = load_op(0);
+  Op op2 = p.n_ops > 1 ? load_op(1) : op1;
   for (long long oi = 0; oi < p.n_ops; oi++) {
-    const Op op = op_next;
-    if (oi + 1 < p.n_ops) op_next = load_op(oi + 1);
+    const Op op = op1;
+    op1 = op2;
+    if (oi + 2 < p.n_ops) op2 = load_op(oi + 2);
+    if (oi + 1 < p.n_ops) prefetch_inputs(op1);
     if (op.kind == 0) {
       // ---- IMU process step: same linearisation / state code as the lane-per-filter kernel ----
       const double* base = p.imu + op.row * 6 * p.imu_cols + imu_n;
@@ -628,8 +658,13 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
       imu_seen = true;
       // the state step only needs the prior state (already captured in L): issued first, its long dependent chain
       // (rsqrt, sin / cos, quaternion product) overlaps the covariance passes
+#if RBIS_GROUP_STATE_FIRST && !defined(RBIS_GROUP_COVONLY)
       state_propagate<true>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
+#endif
       g_cov_propagate<G, DC>(Pf, l, L, qn);
+#if !RBIS_GROUP_STATE_FIRST && !defined(RBIS_GROUP_COVONLY)
+      state_propagate<true>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
+#endif
     } else if (op.kind == 1) {
       // ---- indexed / indexed-plus-orientation measurement ----
       const StreamDesc& st = p.streams[op.stream];
@@ -649,7 +684,9 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
         else if (fast >= 100) g_meas1<G, DC>(Pf, l, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
         else g_meas_block<G, DC>(Pf, l, s, st, a0, st.chunk_len[ci], op.row, sn, dquat, chi0);
       }
+#ifndef RBIS_GROUP_COVONLY
       meas_finish(s, chi0, p.chi_tol, p.ctor_folds_chi, p.renorm);
+#endif
     } else if (op.kind == 2) {
       // ---- snapshot into ring slot ----
       double* d = p.snap + op.row * SNAP_ROWS * N + n;

@@ -125,11 +125,12 @@ __host__ __device__ constexpr int row_of_slot(int s) { return s - col_of_slot(s)
 //   placement 1: the reverse -- the active part (5.5 accesses per slot and step, most values used by several
 //                FMAs) in shared memory, whose loads land in any register, and the passive part (2-3 accesses)
 //                in tensor memory; 113 slots fit in shared memory, so the (b_a,b_a) block and (17,17) stay in TMEM.
+//   placement 3 (DC kernels only, <= 128 filters per CTA): the 120 active slots, all in shared memory.
 //   placement 2 (DC kernels only, 384 filters per CTA): only the 120 active slots are on chip; the 9x9 block of
 //                p, b_g, b_a (45 slots, the least accessed: 1-3 loads and at most one store per step) in tensor
 //                memory, the 75 slots that involve v or chi in shared memory.
 __host__ __device__ constexpr bool on_chip(int i, int j) {
-#if RBIS_PLACEMENT == 2
+#if RBIS_PLACEMENT == 2 || RBIS_PLACEMENT == 3
   return is_act(i) && is_act(j);
 #else
   return true;
@@ -140,6 +141,8 @@ __host__ __device__ constexpr bool slot_in_tm(int i, int j) {
   return is_act(i) && is_act(j);
 #elif RBIS_PLACEMENT == 2
   return ((i >= 9 && !(i >= 12 && i < 15)) && (j >= 9 && !(j >= 12 && j < 15))) || (RBIS_SM_PAIR && i == 5 && j == 20);
+#elif RBIS_PLACEMENT == 3
+  return false;  // DC kernels with <= 128 filters per CTA: all 120 active slots fit in shared memory (123 KB)
 #else
   return !(is_act(i) && is_act(j)) || i >= 18 || (i == 17 && j == 17);
 #endif
