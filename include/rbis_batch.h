@@ -279,6 +279,20 @@ int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* tru
  * the next step. */
 int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int chunk,
                              double* out_chunks, int64_t* n_chunks);
+/* ---- statistics of a SHARDED ensemble: one process per GPU, each handle holds the contiguous filter range
+ * [first_chunk * chunk, first_chunk * chunk + N) of an ensemble of total_chunks chunks.  The shard's chunk partials are written
+ * into its rows of a zero-initialised DEVICE table [total_chunks][RBIS_NUM_STATS], the table is summed over the ranks with
+ * ncclAllReduce on the handle's stream (exact: every row has one non-zero contributor), and reduced on the device in
+ * ascending chunk order -- no host round trip before the collective.  The totals (and the table) are therefore bit-identical
+ * on every rank and for every GPU count, and equal to rbis_batch_stats + rbis_stats_reduce_chunks on one GPU.
+ *   nccl_comm: the caller's ncclComm_t (as void*), one rank per handle, created on the handle's device; NULL = single
+ *              process (no collective; first_chunk = 0, total_chunks = the shard's own count).  The library resolves
+ *              ncclAllReduce from the NCCL already loaded in the calling process and has no link-time NCCL dependency.
+ *   truth_vec [21] / truth_quat [4]: host, shared by all filters.  out_totals: host [RBIS_NUM_STATS].
+ *   out_table: host [total_chunks][RBIS_NUM_STATS] or NULL.  Synchronous (collective: every rank of the communicator calls it). */
+int rbis_batch_stats_allreduce(rbis_batch_t* h, void* nccl_comm, const double* truth_vec, const double* truth_quat, int chunk,
+                               int64_t first_chunk, int64_t total_chunks, double* out_totals, double* out_table);
+
 /* ---- windowed noise-identification likelihood: the per-window term of sampleProcessForward + negLogLikelihood
  * (state-estimator/src/noise_id/noise_id.cpp:36-40,44-65) for every filter at once.  With the
  * filters' heads = states rolled forward over one window from the truth, truth_vec [21][N] / truth_quat [4][N] = the

@@ -318,6 +318,18 @@ class RBISBatch:
         return out, pf
 
 
+    def stats_allreduce(self, comm, truth_vec, truth_quat, first_chunk, total_chunks, chunk=1024, want_table=False):
+        """rbis_batch_stats_allreduce: statistics of a sharded ensemble through a raw NCCL communicator (pronto_b200.nccl.
+        Communicator, or None for a single process) -> (totals [96], table [total_chunks][96] or None)."""
+        tv = np.ascontiguousarray(truth_vec, dtype=np.float64); tq = np.ascontiguousarray(truth_quat, dtype=np.float64)
+        assert tv.size == 21 and tq.size == 4
+        totals = np.zeros(capi.NUM_STATS)
+        table = np.zeros((int(total_chunks), capi.NUM_STATS)) if want_table else None
+        capi.check(self.lib.rbis_batch_stats_allreduce(self.h, comm.handle if comm is not None else None, tv.ctypes.data, tq.ctypes.data,
+                                                       int(chunk), int(first_chunk), int(total_chunks), totals.ctypes.data,
+                                                       table.ctypes.data if want_table else None))
+        return totals, table
+
     def stats_enqueue(self, truth_vec, truth_quat, out_chunks, chunk=1024):
         """Asynchronous statistics into a PINNED host array [n_chunks][96]; valid after wait(record())."""
         tv = np.ascontiguousarray(truth_vec, dtype=np.float64); tq = np.ascontiguousarray(truth_quat, dtype=np.float64)

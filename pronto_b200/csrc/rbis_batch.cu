@@ -2,6 +2,7 @@
 // over the sm_100a kernels in rbis_kernels.cuh / rbis_stats.cuh.  No CPU compute path exists here:
 // every entry point that updates filters launches a CUDA kernel or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -112,6 +113,7 @@ struct rbis_batch {
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
   DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
+  DevBuf stats_table;   // device-resident [total_chunks][96] table + [96] totals of rbis_batch_stats_allreduce
   rbisk::Op* d_ops = nullptr;
   size_t d_ops_cap = 0;
   double* d_rshared = nullptr;  // [MAX_STREAMS][81]
@@ -758,7 +760,7 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag); cudaFree(h->d_notch_state);
   h->notch_stage.release();
   for (auto& m : h->d_map) cudaFree(m);
-  h->full_cov.release(); h->misc.release(); h->stats_async.release();
+  h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release();
   for (auto& s : h->slots) {
     s.imu.release();
     for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }
@@ -1064,6 +1066,69 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
   h->launches++;
   CUDA_TRY(cudaMemcpyAsync(out_chunks, d_chunks, (size_t)nch * RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (n_chunks) *n_chunks = nch;
+  return 0;
+}
+
+// NCCL is taken from the calling process at run time (dlsym): a host that passes an ncclComm_t has NCCL loaded already, and the
+// communicator must belong to that very library; librbis_b200.so itself carries no NCCL dependency.
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
+static nccl_allreduce_fn resolve_nccl_allreduce() {
+  static nccl_allreduce_fn fn = nullptr;
+  if (fn) return fn;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+  if (!sym) {
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      if (void* lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD)) { sym = dlsym(lib, "ncclAllReduce"); if (sym) break; }
+    }
+  }
+  fn = reinterpret_cast<nccl_allreduce_fn>(sym);
+  return fn;
+}
+
+int rbis_batch_stats_allreduce(rbis_batch_t* h, void* nccl_comm, const double* truth_vec, const double* truth_quat, int chunk,
+                               int64_t first_chunk, int64_t total_chunks, double* out_totals, double* out_table) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!truth_vec || !truth_quat || !out_totals) return fail(RBIS_ERR_INVALID, "truth and out_totals are required");
+  if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
+  const size_t N = (size_t)h->N;
+  const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
+  if (first_chunk < 0 || total_chunks < 1 || first_chunk + nch > total_chunks)
+    return fail(RBIS_ERR_INVALID, "chunks %lld..%lld of this shard do not fit a table of %lld chunks", (long long)first_chunk,
+                (long long)(first_chunk + nch), (long long)total_chunks);
+  nccl_allreduce_fn allreduce = nullptr;
+  if (nccl_comm) {
+    allreduce = resolve_nccl_allreduce();
+    if (!allreduce) return fail(RBIS_ERR_STATE, "an NCCL communicator was passed but no NCCL library is loaded in this process (ncclAllReduce not found)");
+  }
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  // device-resident: truth [25] | table [total_chunks][96] | totals [96]
+  const size_t n_table = (size_t)total_chunks * RBIS_NUM_STATS;
+  if (h->stats_table.ensure(32 + n_table + RBIS_NUM_STATS)) return fail(RBIS_ERR_ALLOC, "statistics table allocation failed");
+  double* d_truth = h->stats_table.p;
+  double* d_table = d_truth + 32;
+  double* d_totals = d_table + n_table;
+  double tbuf[25];
+  std::memcpy(tbuf, truth_vec, 21 * sizeof(double));
+  std::memcpy(tbuf + 21, truth_quat, 4 * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(d_truth, tbuf, sizeof(tbuf), cudaMemcpyHostToDevice, h->stream));
+  // every slot of the table has exactly one non-zero contributor (the rank that owns the chunk): the SUM all-reduce is
+  // exact in any order (x + 0 = x), SURVEY.md 8e
+  CUDA_TRY(cudaMemsetAsync(d_table, 0, n_table * sizeof(double), h->stream));
+  rbisk::stats_kernel<<<(unsigned)nch, chunk, chunk * sizeof(double), h->stream>>>(
+      h->vec, h->quat, h->P, h->loglik, d_truth, d_truth + 21, 0, (long long)N, nullptr, d_table + (size_t)first_chunk * RBIS_NUM_STATS);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  if (allreduce) {
+    const int rc = allreduce(d_table, d_table, n_table, /*ncclDouble*/ 8, /*ncclSum*/ 0, nccl_comm, h->stream);
+    if (rc != 0) return fail(RBIS_ERR_CUDA, "ncclAllReduce failed with ncclResult_t %d", rc);
+  }
+  rbisk::reduce_chunk_table_kernel<<<1, 128, 0, h->stream>>>(d_table, (long long)total_chunks, d_totals);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out_totals, d_totals, RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out_table) CUDA_TRY(cudaMemcpyAsync(out_table, d_table, n_table * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

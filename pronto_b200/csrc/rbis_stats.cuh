@@ -100,6 +100,16 @@ __global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ 
   if (t >= 48 && t < NSTAT) out_chunks[(long long)blockIdx.x * NSTAT + t] = 0.0;
 }
 
+// Final reduction of a chunk table on the device: totals[k] = sum over chunks in ASCENDING chunk order (one thread per
+// statistic, a plain sequential sum: the same order as rbis_stats_reduce_chunks on the host).
+__global__ void reduce_chunk_table_kernel(const double* __restrict__ table, long long n_chunks, double* __restrict__ totals) {
+  const int k = threadIdx.x;
+  if (k >= NSTAT) return;
+  double s = 0.0;
+  for (long long c = 0; c < n_chunks; c++) s = __dadd_rn(s, table[c * NSTAT + k]);
+  totals[k] = s;
+}
+
 // ---- windowed noise-identification likelihood (SE/noise_id/noise_id.cpp:36-40,44-65) ----
 // One lane per filter: e = head (-) truth (subtractState + quatToChi), C = cov - base_cov[:, map[n]] (the covariance the
 // same window accumulates under zero process noise), out = log det C_AA + e_A^T C_AA^-1 e_A = -loglike_normalized(e_A, 0, C_AA).
