@@ -18,6 +18,10 @@
  *   - `mem` says where the caller's ensemble arrays live: host memory (copied by the library on the
  *     handle's stream; use pinned memory for truly asynchronous copies) or device memory (used in
  *     place; must stay valid until the call's work has completed).
+ *   - Lifetime of host inputs: a call that takes host arrays with mem == RBIS_MEM_HOST returns once the copies are ENQUEUED
+ *     (pageable memory is staged by the CUDA runtime before the call returns; PINNED memory is read later, by the copy
+ *     engine).  Pinned input arrays of rbis_batch_run_fused must therefore stay valid and unchanged until a later
+ *     rbis_batch_synchronize(), or a rbis_batch_wait() on a ticket recorded after the call, has returned.
  *   - Calls are stream-ordered on the handle and return once enqueued unless stated otherwise;
  *     rbis_batch_synchronize() waits.  A handle is not thread-safe (the reference is single
  *     threaded too: MSE/lcm_front_end.cpp:223-229).
@@ -195,6 +199,48 @@ int rbis_batch_set_column_map(rbis_batch_t* h, int which, const int32_t* map, in
 int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu,
                          int64_t imu_rows, int n_streams, const rbis_stream_t* streams, int mem);
 
+/* ---- on-device synthesis of per-filter sensor streams for Monte-Carlo noise sweeps: every filter reads the
+ * same noise-free log plus its own noise realisation, so the host passes the noise-free rows and a seed and the per-filter
+ * rows are produced in HBM, never crossing PCIe.  Counter-based generator, one draw per (seed, GLOBAL filter index, step
+ * counter, channel): key = seed ^ filter*K1 ^ step*K2 ^ channel*K3, a = splitmix64(key), b = splitmix64(a), Box-Muller.
+ * mode 0 (exact): u1, u2 from 53 bits, sqrt(-2 ln u1) cos(2 pi u2) in double -- pronto_b200/synth.py:normal is its numpy
+ * statement (bit-exact integers, libm calls within an ulp or two); mode 1 (fast): same counters and hash, 24-bit uniforms,
+ * single-precision SFU ln / sqrt / cos.  Channels follow SURVEY.md 8d: 0-2 gyro, 3-5 accelerometer, then per stream. */
+typedef struct {
+  int32_t m;                      /* columns of z */
+  int32_t has_orientation;        /* also draw a measured orientation: mean_quat (x) Exp(sigma_rot * n) */
+  int32_t channel;                /* column a draws channel + a */
+  int32_t channel_rot;            /* the rotation perturbation draws channel_rot + 0..2 */
+  const double* mean;             /* HOST [rows][m] noise-free rows */
+  const double* mean_quat;        /* HOST [rows][4] (w,x,y,z) or NULL */
+  const int64_t* step;            /* HOST [rows] counter value of each row (the global time-step index) */
+  double sigma[RBIS_MAX_MEAS];    /* standard deviation per column */
+  double sigma_rot[3];
+  int64_t rows;
+} rbis_synth_stream_t;
+typedef struct {
+  uint64_t seed;
+  int64_t first_filter;           /* global index of the handle's filter 0: shards of one ensemble draw the same noise for any GPU count */
+  int32_t mode;                   /* 0 exact, 1 fast */
+  int32_t n_streams;
+  const double* imu_mean;         /* HOST [imu_rows][6]: noise-free gyro xyz, accelerometer xyz readings */
+  const int64_t* imu_step;        /* HOST [imu_rows] */
+  int64_t imu_rows;
+  double sigma_gyro, sigma_accel; /* >= 0: standard deviations for all filters; < 0: per filter sqrt(q_gyro / dt), sqrt(q_accel / dt) from
+                                     the handle's process noise, i.e. sample noise consistent with Qd = q dt (MSE/rbis.cpp:116) */
+  double dt;
+  const rbis_synth_stream_t* streams;
+} rbis_synth_t;
+/* Materialise the streams into DEVICE arrays imu_out [imu_rows][6][N], z_out[s] [rows][m][N], quat_out[s] [rows][4][N]
+ * (enqueued on the handle's stream; the host arrays of `syn` are consumed before the call returns).  This is also how a
+ * test feeds the CPU oracle exactly what the device drew. */
+int rbis_batch_synthesize(rbis_batch_t* h, const rbis_synth_t* syn, double* imu_out, double* const* z_out, double* const* quat_out);
+/* rbis_batch_run_fused with synthesised inputs: streams[s].z / .quat / .rows are ignored (taken from syn->streams[s]; a per-filter R
+ * is a DEVICE array on this path), the rows are generated into library-owned device buffers (double buffered across calls) and consumed by the
+ * fused launch.  Host -> device traffic per call: the op list and the noise-free rows. */
+int rbis_batch_run_fused_synth(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, int n_streams, const rbis_stream_t* streams,
+                               const rbis_synth_t* syn);
+
 /* ---- delayed measurements: the batch form of MavStateEstimator::addUpdate's out-of-order insert +
  * replay (MSE/mav_state_est.cpp:28-80) over updateHistory's time-ordered multimap
  * (MSE/update_history.cpp:16-54), for an ensemble whose filters share one arrival schedule.
@@ -305,6 +351,73 @@ int rbis_batch_stats_allreduce(rbis_batch_t* h, void* nccl_comm, const double* t
 int rbis_batch_window_neg_loglik(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, const double* base_cov,
                                  const int32_t* base_map, int64_t base_cols, int n_active, const int32_t* active_idx,
                                  double* out, int mem);
+
+/* ---- wire structs and IMU decode -- host side.  Struct-level layouts of the reference's LCM types;
+ * the LCM byte encoding (big-endian marshalling + fingerprint) is not produced here (no LCM, no lcm-gen, no log to check
+ * an encoder against).
+ * filter_state_t (pronto-lcmtypes/lcmtypes/pronto_filter_state_t.lcm) as rbisCreateFilterStateMessage writes it
+ * (MSE/rbis.cpp:268-285: quat (w,x,y,z), state = vec, cov = Map<RBIM> i.e. COLUMN-major although the .lcm comment says row
+ * major) and RBIS(const pronto_filter_state_t*) reads it (MSE/rbis.hpp:58-67). */
+typedef struct {
+  int64_t utime;
+  double quat[4];
+  int32_t num_states;        /* 21 */
+  int32_t reserved0;
+  double state[RBIS_NUM_STATES];
+  int32_t num_cov_elements;  /* 441 */
+  int32_t reserved1;
+  double cov[RBIS_COV_ELEMS];
+} rbis_filter_state_t;
+/* One message per filter first..first+count-1 (synchronous; reads the whole ensemble: a logging path). */
+int rbis_batch_get_filter_states(rbis_batch_t* h, int64_t first, int64_t count, rbis_filter_state_t* out);
+/* Filters first..first+count-1 := the messages (state, quaternion, covariance; log-likelihood 0), as RBIS(msg) +
+ * Map<const RBIM>(msg->cov) of the reference's log loader (state-estimator/src/noise_id/noise_id.cpp:83-86). */
+int rbis_batch_set_filter_states(rbis_batch_t* h, int64_t first, int64_t count, const rbis_filter_state_t* msgs);
+
+/* indexed_measurement_t (pronto-lcmtypes/lcmtypes/pronto_indexed_measurement_t.lcm), bounded to RBIS_MAX_MEAS rows. */
+typedef struct {
+  int64_t utime, state_utime;
+  int32_t measured_dim;
+  int32_t measured_cov_dim;                      /* measured_dim^2 */
+  double z_effective[RBIS_MAX_MEAS];
+  int32_t z_indices[RBIS_MAX_MEAS];
+  int32_t reserved;
+  double R_effective[RBIS_MAX_MEAS * RBIS_MAX_MEAS];
+} rbis_indexed_measurement_t;
+/* IndexedMeasurementHandler::processMessage (MSE/sensor_handlers.cpp:576-582): the constant part of a stream (index set,
+ * R = Map<MatrixXd>(R_effective, m, m), column-major, copied to R_out[m*m]; sensor_id = indexed_sensor).  z rows are the
+ * messages' z_effective; out->z / rows stay for the caller to fill. */
+int rbis_stream_from_indexed_measurement(const rbis_indexed_measurement_t* msg, rbis_stream_t* out, double* R_out);
+
+/* KVH raw IMU batches of the Atlas INS path.  rbis_kvh_packet_t = bot_core::kvh_raw_imu_t; a batch message carries
+ * num_packets of them, NEWEST FIRST, most of which were already seen in earlier batches.
+ * rbis_kvh_decode_batch = IMUStream::convertFromLCMBatch (estimate_tools/src/estimate_tools/imu_stream.cpp:62-97): the
+ * packets newer than the last one seen come back in out_new, oldest first, with utime_delta = time since the previous new
+ * packet; the others in out_old (optional) with the reference's obfuscated delta; a packet counter that runs backwards
+ * resets the stream.  Both output arrays need room for num_packets entries. */
+typedef struct {
+  int64_t utime;
+  int64_t packet_count;
+  double delta_rotation[3];
+  double linear_acceleration[3];
+} rbis_kvh_packet_t;
+typedef struct {
+  int64_t utime_raw, utime_batch, utime, utime_delta, packet_count;
+  double delta_rotation[3];
+  double linear_acceleration[3];
+} rbis_imu_packet_t;
+typedef struct rbis_kvh_stream rbis_kvh_stream_t;
+int rbis_kvh_stream_create(rbis_kvh_stream_t** out);
+int rbis_kvh_stream_destroy(rbis_kvh_stream_t* s);
+int rbis_kvh_decode_batch(rbis_kvh_stream_t* s, int64_t batch_utime, int32_t num_packets, const rbis_kvh_packet_t* raw,
+                          rbis_imu_packet_t* out_new, int32_t* n_new, rbis_imu_packet_t* out_old, int32_t* n_old);
+/* InsHandler::processMessageAtlas after the decode (MSE/sensor_handlers.cpp:186-251): the newest new packet of a batch
+ * (after the notch cascade, rbis_batch_notch_filter, when the Atlas filter is on) -> gyro = R (delta_rotation / raw_dt),
+ * accel = T linear_acceleration (rotation and translation, as the reference applies bot_trans_apply_vec), and the
+ * integration dt = default_dt for the first message, else the batch utime difference.  *prev_utime: 0 before the first. */
+int rbis_kvh_imu_step(const rbis_imu_packet_t* newest, int64_t batch_utime, const double ins_to_body_quat[4],
+                      const double ins_to_body_trans[3], double default_dt, int64_t* prev_utime, double gyro[3], double accel[3],
+                      double* dt);
 
 /* Stream-ordered completion tickets: record marks "everything enqueued so far", wait blocks the host
  * until that point has completed.  Up to 8 tickets may be outstanding. */

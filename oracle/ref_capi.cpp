@@ -12,6 +12,9 @@
 
 #include <cmath>
 #include <estimate_tools/iir_notch.hpp>  // -I /root/reference/estimate_tools/src
+#include <estimate_tools/imu_stream.hpp>
+#include <list>
+#include <noise_id/noise_id.hpp>          // -I /root/reference/state-estimator/src
 #include "mav_state_est.hpp"  // the reference's headers, found with -I /root/reference/state-estimator/src/mav_state_est
 
 extern "C" int64_t rbis_ref_shim_history_span = 10000000;  // what the BotParam stand-in returns (ref_shim/bot_param)
@@ -254,6 +257,84 @@ void orc_notch_cascade(double notch_freq, double fs, int n_stages, int64_t n, co
   }
   if (state)
     for (int i = 0; i < n_stages; i++) { state[4 * i] = f[i].x(0); state[4 * i + 1] = f[i].x(1); state[4 * i + 2] = f[i].y(0); state[4 * i + 3] = f[i].y(1); }
+}
+
+// ---- the reference's noise identification, state-estimator/src/noise_id/noise_id.cpp:9-65, compiled unmodified ----
+// Same signature as oracle_capi.cpp's restatement: truth history [T1][21], [T1][4], [T1][441] (column-major RBIM per row).
+double orc_noise_id_neg_loglik(int64_t T1, const double* vec, const double* quat, const double* cov, double dt, double q_gyro,
+                               double q_accel, int N_window, int n_active, const int32_t* active, int64_t* n_windows, double* errs) {
+  std::list<RBIS> states;
+  RBIMList covs;
+  for (int64_t t = 0; t < T1; t++) {
+    states.push_back(makeState(vec + 21 * t, quat + 4 * t));
+    covs.push_back(getCov(cov + 441 * t));
+  }
+  std::list<RBIS> errors, rolled;
+  RBIMList ecovs, rolled_covs;
+  sampleProcessForward(states, covs, dt, q_gyro, q_accel, N_window, errors, ecovs, rolled, rolled_covs);
+  if (n_windows) *n_windows = (int64_t)errors.size();
+  if (errs) {
+    size_t w = 0;
+    for (const RBIS& e : errors) { for (int i = 0; i < 21; i++) errs[21 * w + i] = e.vec(i); w++; }
+  }
+  Eigen::VectorXi act(n_active);
+  for (int i = 0; i < n_active; i++) act(i) = active[i];
+  return negLogLikelihood(errors, ecovs, act);
+}
+
+// ---- wire structs: rbisCreateFilterStateMessage (rbis.cpp:268-285) and RBIS(const pronto_filter_state_t*) (rbis.hpp:58-67) ----
+// msg_out: utime, quat[4], num_states, state[21], num_cov_elements, cov[441] flattened into doubles
+// [0] utime, [1..4] quat, [5] num_states, [6..26] state, [27] num_cov_elements, [28..468] cov
+void orc_create_filter_state_message(const double* vec, const double* quat, int64_t utime, const double* cov, double* msg_out) {
+  RBIS s = makeState(vec, quat);
+  s.utime = utime;
+  pronto_filter_state_t* m = rbisCreateFilterStateMessage(s, getCov(cov));
+  msg_out[0] = (double)m->utime;
+  for (int i = 0; i < 4; i++) msg_out[1 + i] = m->quat[i];
+  msg_out[5] = m->num_states;
+  for (int i = 0; i < m->num_states; i++) msg_out[6 + i] = m->state[i];
+  msg_out[27] = m->num_cov_elements;
+  for (int i = 0; i < m->num_cov_elements; i++) msg_out[28 + i] = m->cov[i];
+  free(m->state); free(m->cov); free(m);
+}
+void orc_rbis_from_filter_state(const double* msg, double* vec, double* quat, int64_t* utime) {
+  pronto_filter_state_t m;
+  m.utime = (int64_t)msg[0];
+  for (int i = 0; i < 4; i++) m.quat[i] = msg[1 + i];
+  m.num_states = (int32_t)msg[5];
+  std::vector<double> st(msg + 6, msg + 27), cv(msg + 28, msg + 469);
+  m.state = st.data(); m.num_cov_elements = (int32_t)msg[27]; m.cov = cv.data();
+  RBIS s(&m);
+  putState(s, vec, quat);
+  *utime = s.utime;
+}
+
+// ---- IMUStream::convertFromLCMBatch (estimate_tools/src/estimate_tools/imu_stream.cpp:62-97), stateful over calls ----
+// packets [n][8]: utime, packet_count, delta_rotation[3], linear_acceleration[3] in MESSAGE order (newest first).
+// out_new / out_old [cap][10]: utime_raw, utime_batch, utime, utime_delta, packet_count + 0 pad... see below
+static IMUStream* g_stream = nullptr;
+void orc_kvh_reset() { delete g_stream; g_stream = new IMUStream(); }
+int orc_kvh_decode(int64_t batch_utime, int n, const double* packets, double* out_new, int* n_new, double* out_old, int* n_old) {
+  if (!g_stream) g_stream = new IMUStream();
+  bot_core::kvh_raw_imu_batch_t msg;
+  msg.utime = batch_utime;
+  msg.num_packets = n;
+  for (int i = 0; i < n; i++) {
+    bot_core::kvh_raw_imu_t p;
+    p.utime = (int64_t)packets[8 * i]; p.packet_count = (int64_t)packets[8 * i + 1];
+    for (int k = 0; k < 3; k++) { p.delta_rotation[k] = packets[8 * i + 2 + k]; p.linear_acceleration[k] = packets[8 * i + 5 + k]; }
+    msg.raw_imu.push_back(p);
+  }
+  IMUBatch b = g_stream->convertFromLCMBatch(&msg);
+  auto put = [](const IMUPacket& p, double* o) {
+    o[0] = (double)p.utime_raw; o[1] = (double)p.utime_batch; o[2] = (double)p.utime; o[3] = (double)p.utime_delta; o[4] = (double)p.packet_count;
+    for (int k = 0; k < 3; k++) { o[5 + k] = p.delta_rotation[k]; o[8 + k] = p.linear_acceleration[k]; }
+  };
+  *n_new = (int)b.packets.size();
+  *n_old = (int)b.packets_old.size();
+  for (int i = 0; i < *n_new; i++) put(b.packets[i], out_new + 11 * i);
+  for (int i = 0; i < *n_old; i++) put(b.packets_old[i], out_old + 11 * i);
+  return g_stream->getNumberBatchSinceReset();
 }
 
 }  // extern "C"

@@ -156,4 +156,30 @@ inline std::ostream& operator<<(std::ostream& os, const RigidBodyState& s) {
   return os << s.vec.transpose() << " | " << s.quat.w() << " " << s.quat.x() << " " << s.quat.y() << " " << s.quat.z();
 }
 
+
+// ---- what state-estimator/src/noise_id/noise_id.cpp uses ([RECALLED] eigen_utils/eigen_select_block.hpp, eigen_numerical.hpp) ----
+template <class M, class IR, class IC>
+Eigen::MatrixXd selectBlockByIndices(const Eigen::MatrixBase<M>& m, const Eigen::MatrixBase<IR>& rows, const Eigen::MatrixBase<IC>& cols) {
+  Eigen::MatrixXd out(rows.rows(), cols.rows());
+  for (int i = 0; i < rows.rows(); i++)
+    for (int j = 0; j < cols.rows(); j++) out(i, j) = m.coeff(rows.coeff(i, 0), cols.coeff(j, 0));
+  return out;
+}
+template <class M, class IR>
+Eigen::VectorXd selectRowsByIndices(const Eigen::MatrixBase<M>& m, const Eigen::MatrixBase<IR>& rows) {
+  Eigen::VectorXd out(rows.rows());
+  for (int i = 0; i < rows.rows(); i++) out(i) = m.coeff(rows.coeff(i, 0), 0);
+  return out;
+}
+// log of a Gaussian density without its constant: -log det(sigma) - (mu - x)^T sigma^-1 (mu - x)   (same form as MSE/rbis.cpp:142)
+template <class X, class MU, class S>
+double loglike_normalized(const Eigen::MatrixBase<X>& x, const Eigen::MatrixBase<MU>& mu, const Eigen::MatrixBase<S>& sigma) {
+  Eigen::VectorXd diff = mu - x;
+  Eigen::MatrixXd sg = sigma;
+  Eigen::VectorXd sol = sg.ldlt().solve(diff);
+  double q = 0;
+  for (int i = 0; i < diff.rows(); i++) q += diff(i) * sol(i);
+  return -std::log(sg.determinant()) - q;
+}
+
 }  // namespace eigen_utils

@@ -218,6 +218,10 @@ class Matrix : public WritableBase<Matrix<T, R, C> > {
     static_assert(R * C == 3, "3-coefficient constructor");
     d_[0] = x; d_[1] = y; d_[2] = z;
   }
+  explicit Matrix(const T* p) : r_(R), c_(C), d_((size_t)R * C) {  // fixed-size matrix from a coefficient array (Eigen: Vector3d(ptr))
+    static_assert(R != Dynamic && C != Dynamic, "pointer constructor needs a fixed size");
+    for (size_t k = 0; k < d_.size(); k++) d_[k] = p[k];
+  }
   template <class O>
   Matrix(const MatrixBase<O>& o) : r_(o.rows()), c_(o.cols()), d_((size_t)o.rows() * o.cols()) {
     assert((R == Dynamic || R == r_) && (C == Dynamic || C == c_));
@@ -244,6 +248,8 @@ class Matrix : public WritableBase<Matrix<T, R, C> > {
   void resize(int r, int c = 1) { resize_like(r, c); }
   T* data() { return d_.data(); }
   const T* data() const { return d_.data(); }
+  T& operator[](int i) { return d_[(size_t)i]; }   // vectors only
+  const T& operator[](int i) const { return d_[(size_t)i]; }
 
   static Matrix Zero() { return Matrix(); }
   static Matrix Zero(int r, int c = 1) { return Matrix(r, c); }
@@ -628,6 +634,7 @@ class LLT {
 template <typename T, int R, int C>
 LLT<Matrix<T, R, C> > Matrix<T, R, C>::llt() const { return LLT<Matrix>(*this); }
 
+template <class T> using aligned_allocator = std::allocator<T>;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, Dynamic, 1> VectorXd;

@@ -57,6 +57,53 @@ class MeasStream:
         self.sensor_id = int(sensor_id)
 
 
+class SynthSpec:
+    """Noise-free rows + noise description of one time chunk (rbis_synth_t): what rbis_batch_run_fused_synth /
+    rbis_batch_synthesize turn into per-filter input rows on the device.
+
+    imu_mean [rows][6], imu_step [rows]; streams: list of dicts with mean [rows][m], step [rows], sigma [m], channel and,
+    for orientation streams, mean_quat [rows][4], sigma_rot [3], channel_rot.  sigma_gyro / sigma_accel < 0: per filter
+    sqrt(q / dt) from the handle's process noise."""
+
+    def __init__(self, seed, imu_mean, imu_step, streams=(), sigma_gyro=-1.0, sigma_accel=-1.0, dt=1e-3, mode=0, first_filter=0):
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i8 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        self.keep = []
+        self.c = capi.Synth()
+        self.c.seed, self.c.first_filter, self.c.mode = int(seed) & (2 ** 64 - 1), int(first_filter), int(mode)
+        im, ist = f8(imu_mean).reshape(-1, 6), i8(imu_step).reshape(-1)
+        assert im.shape[0] == ist.shape[0]
+        self.keep += [im, ist]
+        self.c.imu_mean, self.c.imu_step, self.c.imu_rows = im.ctypes.data, ist.ctypes.data, im.shape[0]
+        self.c.sigma_gyro, self.c.sigma_accel, self.c.dt = float(sigma_gyro), float(sigma_accel), float(dt)
+        self.sarr = (capi.SynthStream * max(1, len(streams)))()
+        self.shapes = []
+        for k, st in enumerate(streams):
+            mean = f8(st["mean"])
+            rows, m = mean.shape
+            step = i8(st["step"]).reshape(-1)
+            assert step.shape[0] == rows
+            d = self.sarr[k]
+            d.m, d.channel, d.rows = m, int(st["channel"]), rows
+            d.mean, d.step = mean.ctypes.data, step.ctypes.data
+            sig = np.broadcast_to(np.asarray(st["sigma"], dtype=np.float64), (m,))
+            for a in range(m):
+                d.sigma[a] = float(sig[a])
+            self.keep += [mean, step]
+            mq = st.get("mean_quat")
+            d.has_orientation = int(mq is not None)
+            if mq is not None:
+                mq = f8(mq).reshape(rows, 4)
+                d.mean_quat, d.channel_rot = mq.ctypes.data, int(st["channel_rot"])
+                sr = np.broadcast_to(np.asarray(st["sigma_rot"], dtype=np.float64), (3,))
+                for a in range(3):
+                    d.sigma_rot[a] = float(sr[a])
+                self.keep.append(mq)
+            self.shapes.append((rows, m, mq is not None))
+        self.c.n_streams = len(streams)
+        self.c.streams = self.sarr
+
+
 def make_ops(entries):
     """entries: iterable of (kind, stream, row, utime, dt) -> structured numpy op array."""
     entries = list(entries)
@@ -236,8 +283,9 @@ class RBISBatch:
         return getattr(self, "_cols", {}).get(int(which) + 1, self.N)
 
     # ---- fused program ----
-    def run_fused(self, ops, imu=None, streams=()):
-        """ops: structured array (OP_DTYPE) or iterable of (kind, stream, row, utime, dt)."""
+    def prepare_fused(self, ops, imu=None, streams=()):
+        """Marshal one rbis_batch_run_fused call once (ctypes structures, pointer checks); run_prepared() then costs one foreign
+        call.  The arrays are referenced by the returned object and must keep their contents until the launch has run."""
         if not (isinstance(ops, np.ndarray) and ops.dtype == OP_DTYPE):
             ops = make_ops(ops)
         ops = np.ascontiguousarray(ops)
@@ -273,13 +321,72 @@ class RBISBatch:
                 d.R = R.ctypes.data
             keep.append(st)
         mem = _common_mem(mems, "run_fused")
-        # host inputs must outlive their asynchronous copies: hold the last few calls' arrays
-        self._keep_ring = (getattr(self, "_keep_ring", []) + [keep])[-4:]
-        capi.check(self.lib.rbis_batch_run_fused(self.h, len(ops), ops.ctypes.data_as(C.POINTER(capi.Op)), p_imu,
-                                                 imu_rows, len(streams), sarr, mem))
+        return (len(ops), ops.ctypes.data_as(C.POINTER(capi.Op)), p_imu, imu_rows, len(streams), sarr, mem, keep)
+
+    def run_prepared(self, prep):
+        capi.check(self.lib.rbis_batch_run_fused(self.h, *prep[:7]))
+
+    def run_fused(self, ops, imu=None, streams=()):
+        """ops: structured array (OP_DTYPE) or iterable of (kind, stream, row, utime, dt)."""
+        prep = self.prepare_fused(ops, imu, streams)
+        # host inputs must outlive their asynchronous copies (rbis_batch.h, "lifetime of host inputs"): every call's arrays are
+        # held until a later synchronize() / wait() has shown that the copies ran
+        self._pending_keep = getattr(self, "_pending_keep", [])
+        self._pending_keep.append(prep)
+        if len(self._pending_keep) > 64:   # bounded: beyond this many un-synchronised calls, drain
+            self.synchronize()
+        self.run_prepared(prep)
+
+    def run_fused_synth(self, ops, streams, spec):
+        """rbis_batch_run_fused_synth: `streams` carry idx / R (z, quat ignored: MeasStream(idx, None, R, quat=True/None)),
+        `spec` (SynthSpec) the noise-free rows; per-filter input rows are generated on the device."""
+        if not (isinstance(ops, np.ndarray) and ops.dtype == OP_DTYPE):
+            ops = make_ops(ops)
+        ops = np.ascontiguousarray(ops)
+        sarr = (capi.Stream * max(1, len(streams)))()
+        keep = [ops, spec]
+        for s, st in enumerate(streams):
+            m = len(st.idx)
+            d = sarr[s]
+            d.m, d.has_orientation, d.sensor_id = m, int(st.quat is not None), st.sensor_id
+            d.r_mode = capi.R_PER_FILTER_DIAG if st.per_filter_diag else capi.R_SHARED_FULL
+            for a, i in enumerate(st.idx):
+                d.idx[a] = i
+            if st.per_filter_diag:
+                d.R, mm = _ptr(st.R, (m, self.N), "R")
+                if mm != capi.MEM_DEVICE:
+                    raise ValueError("run_fused_synth: a per-filter R must be a device tensor")
+            else:
+                R = np.ascontiguousarray(np.asarray(st.R, dtype=np.float64).reshape(m, m).T)
+                keep.append(R)
+                d.R = R.ctypes.data
+            keep.append(st)
+        self._pending_keep = getattr(self, "_pending_keep", [])
+        self._pending_keep.append(keep)
+        capi.check(self.lib.rbis_batch_run_fused_synth(self.h, len(ops), ops.ctypes.data_as(C.POINTER(capi.Op)), len(streams), sarr,
+                                                       C.byref(spec.c)))
+
+    def synthesize(self, spec):
+        """rbis_batch_synthesize -> dict(imu [rows][6][N], z [list], quat [list]) as torch CUDA tensors (what the device draws)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        imu = torch.empty((int(spec.c.imu_rows), 6, self.N), dtype=torch.float64, device=dev)
+        zs, qs = [], []
+        zp = (C.c_void_p * max(1, len(spec.shapes)))()
+        qp = (C.c_void_p * max(1, len(spec.shapes)))()
+        for k, (rows, m, orient) in enumerate(spec.shapes):
+            zs.append(torch.empty((rows, m, self.N), dtype=torch.float64, device=dev))
+            qs.append(torch.empty((rows, 4, self.N), dtype=torch.float64, device=dev) if orient else None)
+            zp[k] = zs[k].data_ptr()
+            qp[k] = qs[k].data_ptr() if orient else None
+        capi.check(self.lib.rbis_batch_synthesize(self.h, C.byref(spec.c), imu.data_ptr(), zp, qp))
+        self.synchronize()
+        return dict(imu=imu, z=zs, quat=qs)
 
     def synchronize(self):
         capi.check(self.lib.rbis_batch_synchronize(self.h))
+        self._pending_keep = []   # every copy enqueued so far has run
 
     @property
     def launch_count(self):

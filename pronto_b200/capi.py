@@ -54,6 +54,58 @@ class Stream(C.Structure):
     ]
 
 
+class SynthStream(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32),
+        ("has_orientation", C.c_int32),
+        ("channel", C.c_int32),
+        ("channel_rot", C.c_int32),
+        ("mean", C.c_void_p),
+        ("mean_quat", C.c_void_p),
+        ("step", C.c_void_p),
+        ("sigma", C.c_double * MAX_MEAS),
+        ("sigma_rot", C.c_double * 3),
+        ("rows", C.c_int64),
+    ]
+
+
+class Synth(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("first_filter", C.c_int64),
+        ("mode", C.c_int32),
+        ("n_streams", C.c_int32),
+        ("imu_mean", C.c_void_p),
+        ("imu_step", C.c_void_p),
+        ("imu_rows", C.c_int64),
+        ("sigma_gyro", C.c_double),
+        ("sigma_accel", C.c_double),
+        ("dt", C.c_double),
+        ("streams", C.POINTER(SynthStream)),
+    ]
+
+
+class FilterState(C.Structure):
+    _fields_ = [("utime", C.c_int64), ("quat", C.c_double * 4), ("num_states", C.c_int32), ("reserved0", C.c_int32),
+                ("state", C.c_double * NUM_STATES), ("num_cov_elements", C.c_int32), ("reserved1", C.c_int32),
+                ("cov", C.c_double * COV_ELEMS)]
+
+
+class IndexedMeasurement(C.Structure):
+    _fields_ = [("utime", C.c_int64), ("state_utime", C.c_int64), ("measured_dim", C.c_int32), ("measured_cov_dim", C.c_int32),
+                ("z_effective", C.c_double * MAX_MEAS), ("z_indices", C.c_int32 * MAX_MEAS), ("reserved", C.c_int32),
+                ("R_effective", C.c_double * (MAX_MEAS * MAX_MEAS))]
+
+
+class KvhPacket(C.Structure):
+    _fields_ = [("utime", C.c_int64), ("packet_count", C.c_int64), ("delta_rotation", C.c_double * 3), ("linear_acceleration", C.c_double * 3)]
+
+
+class ImuPacket(C.Structure):
+    _fields_ = [("utime_raw", C.c_int64), ("utime_batch", C.c_int64), ("utime", C.c_int64), ("utime_delta", C.c_int64),
+                ("packet_count", C.c_int64), ("delta_rotation", C.c_double * 3), ("linear_acceleration", C.c_double * 3)]
+
+
 class Op(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -91,6 +143,15 @@ PROTOTYPES = {
     "rbis_batch_indexed_orient_update": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "rbis_batch_set_column_map": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "rbis_batch_run_fused": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Op), C.c_void_p, C.c_int64, C.c_int, C.POINTER(Stream), C.c_int]),
+    "rbis_batch_synthesize": (C.c_int, [C.c_void_p, C.POINTER(Synth), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rbis_batch_run_fused_synth": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Op), C.c_int, C.POINTER(Stream), C.POINTER(Synth)]),
+    "rbis_batch_get_filter_states": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(FilterState)]),
+    "rbis_batch_set_filter_states": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(FilterState)]),
+    "rbis_stream_from_indexed_measurement": (C.c_int, [C.POINTER(IndexedMeasurement), C.POINTER(Stream), C.c_void_p]),
+    "rbis_kvh_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "rbis_kvh_stream_destroy": (C.c_int, [C.c_void_p]),
+    "rbis_kvh_decode_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(KvhPacket), C.POINTER(ImuPacket), c_int32_p, C.POINTER(ImuPacket), c_int32_p]),
+    "rbis_kvh_imu_step": (C.c_int, [C.POINTER(ImuPacket), C.c_int64, c_double_p, c_double_p, C.c_double, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "rbis_planner_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]),
     "rbis_planner_destroy": (C.c_int, [C.c_void_p]),
     "rbis_planner_add_update": (C.c_int, [C.c_void_p, C.POINTER(Op), C.c_int]),

@@ -16,6 +16,7 @@
 #include "rbis_kernels.cuh"   // namespace rbisk: the DENSE lane-per-filter kernels (256 filters per CTA, whole covariance on chip)
 #include "rbis_stats.cuh"
 #include "rbis_smooth.cuh"
+#include "rbis_synth.cuh"
 // The other fused-kernel configurations live in translation units of their own (rbis_fused_*.cu over rbis_fused_tu.inc):
 // the decoupled lane-per-filter kernels at 384 / 256 / 128 filters per CTA and the warp-group kernels of rbis_group.cuh.
 #include "rbis_fused_tu.h"
@@ -113,6 +114,7 @@ struct rbis_batch {
   DevBuf full_cov;      // [441][N] scratch for set/get_state
   DevBuf misc;          // small scratch
   DevBuf stats_async;   // scratch of rbis_batch_stats_enqueue
+  DevBuf synth_small;   // device copies of the noise-free rows and counters of rbis_batch_synthesize
   DevBuf stats_table;   // device-resident [total_chunks][96] table + [96] totals of rbis_batch_stats_allreduce
   rbisk::Op* d_ops = nullptr;
   size_t d_ops_cap = 0;
@@ -133,6 +135,15 @@ struct rbis_batch {
   bool gdone_valid[kRing] = {};
   cudaEvent_t uploaded[kRing] = {};
   cudaEvent_t pre_evt = nullptr;
+  cudaEvent_t syn_evt = nullptr;
+  // ---- pinned host ring for the small per-call uploads (op table, shared R matrices, noise-free synth rows): a
+  // cudaMemcpyAsync from PAGEABLE memory makes the host wait until the stream has drained to the copy, which would stop
+  // the host from running ahead of the device; from pinned memory it is truly asynchronous.
+  static constexpr int kPinSlots = 16;
+  static constexpr size_t kPinBytes = 128 << 10;
+  char* pin_base = nullptr;
+  cudaEvent_t pin_evt[kPinSlots] = {};
+  int pin_next = 0;
   rbisk::Op* d_ops_ring[kRing] = {};
   size_t d_ops_ring_cap[kRing] = {};
   double* d_rshared_ring[kRing] = {};
@@ -351,6 +362,23 @@ void plan_chunks(int m, int r_mode, const double* R_host, rbisk::StreamDesc& d) 
   }
 }
 
+// cudaMemcpyAsync of a small host block through the handle's pinned ring (falls back to the pageable copy when it does not fit)
+int upload_small(rbis_batch* h, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (!h->pin_base || bytes > rbis_batch::kPinBytes) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  const int k = h->pin_next;
+  h->pin_next = (k + 1) % rbis_batch::kPinSlots;
+  CUDA_TRY(cudaEventSynchronize(h->pin_evt[k]));  // the copy that last used this slot (16 uploads ago) has run
+  char* p = h->pin_base + (size_t)k * rbis_batch::kPinBytes;
+  std::memcpy(p, src, bytes);
+  CUDA_TRY(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(h->pin_evt[k], st));
+  return 0;
+}
+
 int copy_in(rbis_batch* h, DevBuf& buf, const double* src, size_t count, int mem, cudaStream_t st,
             const double** out) {
   if (mem == RBIS_MEM_DEVICE) {
@@ -375,9 +403,16 @@ int validate_stream(int s, const rbis_stream_t& in) {
   return 0;
 }
 
-// dry_run: validate the whole call (ops, streams) and return without enqueueing anything
+}  // namespace
+extern "C" int synthesize_into(rbis_batch_t* h, const rbis_synth_t* syn, double* imu_out, double* const* z_out, double* const* quat_out, cudaStream_t stream);
+namespace {
+
+// dry_run: validate the whole call (ops, streams) and return without enqueueing anything.
+// syn != nullptr: the input rows are synthesised on the device into the staging slot (rbis_batch_run_fused_synth) instead of
+// being copied from the host; everything else -- double buffering, overlap with the previous launch -- is the host path's.
 int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
-                 int n_streams, const rbis_stream_t* streams, int mem, bool use_maps = true, bool dry_run = false) {
+                 int n_streams, const rbis_stream_t* streams_in, int mem, bool use_maps = true, bool dry_run = false,
+                 const rbis_synth_t* syn = nullptr) {
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(RBIS_ERR_INVALID, "bad op list");
   if (n_streams < 0 || n_streams > RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "n_streams out of range");
@@ -385,6 +420,25 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (n_ops == 0) return 0;
   if (int rc = use_device(h)) return rc;
   const int64_t N = h->N;
+  std::vector<rbis_stream_t> stream_copy;
+  const rbis_stream_t* streams = streams_in;
+  if (syn) {
+    // rows come from the synth description; z / quat pointers are filled in below once the staging buffers exist
+    if (n_streams != syn->n_streams) return fail(RBIS_ERR_INVALID, "n_streams differs from syn->n_streams");
+    stream_copy.assign(streams_in, streams_in + n_streams);
+    for (int s = 0; s < n_streams; s++) {
+      const rbis_synth_stream_t& ss = syn->streams[s];
+      if (ss.m != stream_copy[s].m || (ss.has_orientation != 0) != (stream_copy[s].has_orientation != 0))
+        return fail(RBIS_ERR_INVALID, "stream %d: synth description does not match the stream", s);
+      stream_copy[s].rows = ss.rows;
+      stream_copy[s].z = reinterpret_cast<const double*>(8);     // placeholders for validation; replaced below
+      stream_copy[s].quat = ss.has_orientation ? reinterpret_cast<const double*>(8) : nullptr;
+    }
+    streams = stream_copy.data();
+    imu = syn->imu_rows > 0 ? reinterpret_cast<const double*>(8) : nullptr;
+    imu_rows = syn->imu_rows;
+    mem = RBIS_MEM_DEVICE;  // per-filter R arrays are device arrays on this path
+  }
 
   // ---- validate ops and translate ----
   std::vector<rbisk::Op> kops((size_t)n_ops);
@@ -449,7 +503,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   StagingSlot& slot = h->slots[h->slot_toggle];
   h->slot_toggle ^= 1;
   cudaStream_t cst = h->copy_stream;
-  const bool staging = (mem == RBIS_MEM_HOST);
+  const bool staging = (mem == RBIS_MEM_HOST) || syn != nullptr;
   const bool grouped = h->n_groups > 1;
   const int ring = (int)(h->launch_seq % rbis_batch::kRing);
   if (staging) {
@@ -464,6 +518,33 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   }
   kp.imu_map = use_maps ? h->d_map[0] : nullptr;
   kp.imu_cols = kp.imu_map ? h->map_cols[0] : N;
+  if (syn) {
+    // synthesise this call's rows into the staging slot, on the copy stream (ordered after everything the main stream has
+    // enqueued so far: the process-noise arrays the IMU synthesis may read)
+    if (kp.imu_map) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
+    for (int s = 0; s < n_streams; s++)
+      if (use_maps && h->d_map[1 + s]) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
+    double* z_out[RBIS_MAX_STREAMS] = {};
+    double* q_out[RBIS_MAX_STREAMS] = {};
+    if (imu_rows > 0 && slot.imu.ensure((size_t)imu_rows * 6 * (size_t)N)) return fail(RBIS_ERR_ALLOC, "synth IMU buffer allocation failed");
+    for (int s = 0; s < n_streams; s++) {
+      const rbis_synth_stream_t& ss = syn->streams[s];
+      if (ss.rows == 0) continue;
+      if (slot.z[s].ensure((size_t)ss.rows * ss.m * (size_t)N)) return fail(RBIS_ERR_ALLOC, "synth buffer allocation failed");
+      z_out[s] = slot.z[s].p;
+      stream_copy[s].z = z_out[s];
+      if (ss.has_orientation) {
+        if (slot.quat[s].ensure((size_t)ss.rows * 4 * (size_t)N)) return fail(RBIS_ERR_ALLOC, "synth buffer allocation failed");
+        q_out[s] = slot.quat[s].p;
+        stream_copy[s].quat = q_out[s];
+      }
+    }
+    if (!h->syn_evt) CUDA_TRY(cudaEventCreateWithFlags(&h->syn_evt, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(h->syn_evt, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(cst, h->syn_evt, 0));
+    if (int rc = synthesize_into(h, syn, slot.imu.p, z_out, q_out, cst)) return rc;
+    imu = slot.imu.p;
+  }
   if (imu) {
     if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * (size_t)kp.imu_cols, mem, cst, &kp.imu)) return rc;
   }
@@ -534,9 +615,9 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaMalloc(&h->d_ops, cap * sizeof(rbisk::Op)));
       h->d_ops_cap = cap;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = upload_small(h, h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), h->stream)) return rc;
     if (any_shared)
-      CUDA_TRY(cudaMemcpyAsync(h->d_rshared, rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      if (int rc = upload_small(h, h->d_rshared, rshared.data(), rshared.size() * sizeof(double), h->stream)) return rc;
     kp.ops = h->d_ops;
     kp.block_offset = 0;
     CUDA_TRY(launch_variant(variant, geom, grid, h->stream, kp));
@@ -553,9 +634,9 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       CUDA_TRY(cudaMalloc(&h->d_ops_ring[ring], cap * sizeof(rbisk::Op)));
       h->d_ops_ring_cap[ring] = cap;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->d_ops_ring[ring], kops.data(), (size_t)n_ops * sizeof(rbisk::Op), cudaMemcpyHostToDevice, h->upload_stream));
+    if (int rc = upload_small(h, h->d_ops_ring[ring], kops.data(), (size_t)n_ops * sizeof(rbisk::Op), h->upload_stream)) return rc;
     if (any_shared)
-      CUDA_TRY(cudaMemcpyAsync(h->d_rshared_ring[ring], rshared.data(), rshared.size() * sizeof(double), cudaMemcpyHostToDevice, h->upload_stream));
+      if (int rc = upload_small(h, h->d_rshared_ring[ring], rshared.data(), rshared.size() * sizeof(double), h->upload_stream)) return rc;
     CUDA_TRY(cudaEventRecord(h->uploaded[ring], h->upload_stream));
     kp.ops = h->d_ops_ring[ring];
     const bool wait_main = h->stream_dirty;
@@ -709,6 +790,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     CREATE_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
   }
   for (auto& t : h->tickets) CREATE_TRY(cudaEventCreateWithFlags(&t, cudaEventDisableTiming));
+  CREATE_TRY(cudaMallocHost(&h->pin_base, rbis_batch::kPinSlots * rbis_batch::kPinBytes));
+  for (auto& e : h->pin_evt) CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CREATE_TRY(cudaMalloc(&h->vec, N * 21 * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->quat, N * 4 * sizeof(double)));
   CREATE_TRY(cudaMalloc(&h->P, N * rbisk::NP * sizeof(double)));
@@ -756,11 +839,15 @@ int rbis_batch_destroy(rbis_batch_t* h) {
     cudaFree(h->d_rshared_ring[r]);
   }
   if (h->pre_evt) cudaEventDestroy(h->pre_evt);
+  if (h->syn_evt) cudaEventDestroy(h->syn_evt);
+  for (auto& e : h->pin_evt)
+    if (e) cudaEventDestroy(e);
+  if (h->pin_base) cudaFreeHost(h->pin_base);
   cudaFree(h->vec); cudaFree(h->quat); cudaFree(h->P); cudaFree(h->loglik); cudaFree(h->qparams);
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag); cudaFree(h->d_notch_state);
   h->notch_stage.release();
   for (auto& m : h->d_map) cudaFree(m);
-  h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release();
+  h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release(); h->synth_small.release();
   for (auto& s : h->slots) {
     s.imu.release();
     for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }
@@ -963,6 +1050,88 @@ int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, c
     return 0;
   }
   return launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem);
+}
+
+// Enqueue the synthesis kernels on the main stream: imu_out [imu_rows][6][N], z_out[s] [rows][m][N], quat_out[s] [rows][4][N]
+// are DEVICE arrays.
+__attribute__((visibility("hidden"))) int synthesize_into(rbis_batch_t* h, const rbis_synth_t* syn, double* imu_out, double* const* z_out, double* const* quat_out, cudaStream_t stream) {
+  if (!syn) return fail(RBIS_ERR_INVALID, "syn is NULL");
+  if (syn->mode != 0 && syn->mode != 1) return fail(RBIS_ERR_INVALID, "synth mode must be 0 (exact) or 1 (fast)");
+  if (syn->n_streams < 0 || syn->n_streams > RBIS_MAX_STREAMS || (syn->n_streams > 0 && !syn->streams)) return fail(RBIS_ERR_INVALID, "bad synth streams");
+  if (syn->imu_rows < 0 || (syn->imu_rows > 0 && (!syn->imu_mean || !syn->imu_step || !imu_out))) return fail(RBIS_ERR_INVALID, "bad synth IMU description");
+  if ((syn->sigma_gyro < 0 || syn->sigma_accel < 0) && !(syn->dt > 0)) return fail(RBIS_ERR_INVALID, "per-filter IMU noise needs dt > 0");
+  const long long N = h->N;
+  // one small host block -> device: [imu_mean | imu_step | per stream: mean, mean_quat, step]
+  size_t words = (size_t)syn->imu_rows * 7;
+  for (int s = 0; s < syn->n_streams; s++) {
+    const rbis_synth_stream_t& st = syn->streams[s];
+    if (st.m < 1 || st.m > RBIS_MAX_MEAS || st.rows < 0) return fail(RBIS_ERR_INVALID, "synth stream %d: bad m / rows", s);
+    if (st.rows > 0 && (!st.mean || !st.step || !z_out || !z_out[s])) return fail(RBIS_ERR_INVALID, "synth stream %d: mean, step and an output array are required", s);
+    if (st.has_orientation && st.rows > 0 && (!st.mean_quat || !quat_out || !quat_out[s])) return fail(RBIS_ERR_INVALID, "synth stream %d: mean_quat and a quaternion output are required", s);
+    words += (size_t)st.rows * (st.m + 1 + (st.has_orientation ? 4 : 0));
+  }
+  if (words == 0) return 0;
+  std::vector<double> host(words);
+  size_t off = 0;
+  auto put = [&](const void* src, size_t n_words) { std::memcpy(host.data() + off, src, n_words * 8); off += n_words; return off - n_words; };
+  const size_t o_imu = put(syn->imu_mean, (size_t)syn->imu_rows * 6), o_istep = put(syn->imu_step, (size_t)syn->imu_rows);
+  size_t o_mean[RBIS_MAX_STREAMS] = {}, o_q[RBIS_MAX_STREAMS] = {}, o_step[RBIS_MAX_STREAMS] = {};
+  for (int s = 0; s < syn->n_streams; s++) {
+    const rbis_synth_stream_t& st = syn->streams[s];
+    o_mean[s] = put(st.mean, (size_t)st.rows * st.m);
+    if (st.has_orientation) o_q[s] = put(st.mean_quat, (size_t)st.rows * 4);
+    o_step[s] = put(st.step, (size_t)st.rows);
+  }
+  // the previous call's kernels may still read the small block: it is rewritten on the same stream, after them
+  if (h->synth_small.cap < words) CUDA_TRY(cudaStreamSynchronize(stream));
+  if (h->synth_small.ensure(words)) return fail(RBIS_ERR_ALLOC, "synth scratch allocation failed");
+  double* d = h->synth_small.p;
+  if (int rc = upload_small(h, d, host.data(), words * 8, stream)) return rc;
+  const unsigned gx = (unsigned)((N + 255) / 256);
+  if (syn->imu_rows > 0) {
+    const dim3 grid(gx, (unsigned)syn->imu_rows);
+    if (syn->mode == 0)
+      rbisk::synth_imu_kernel<0><<<grid, 256, 0, stream>>>(imu_out, d + o_imu, reinterpret_cast<const long long*>(d + o_istep), syn->imu_rows, N, syn->seed,
+                                                              syn->first_filter, syn->sigma_gyro, syn->sigma_accel, h->qparams, h->qparams + N, syn->dt);
+    else
+      rbisk::synth_imu_kernel<1><<<grid, 256, 0, stream>>>(imu_out, d + o_imu, reinterpret_cast<const long long*>(d + o_istep), syn->imu_rows, N, syn->seed,
+                                                              syn->first_filter, syn->sigma_gyro, syn->sigma_accel, h->qparams, h->qparams + N, syn->dt);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  for (int s = 0; s < syn->n_streams; s++) {
+    const rbis_synth_stream_t& st = syn->streams[s];
+    if (st.rows == 0) continue;
+    rbisk::SynStreamDev sd;
+    std::memset(&sd, 0, sizeof(sd));
+    sd.m = st.m; sd.has_orient = st.has_orientation ? 1 : 0; sd.channel = st.channel; sd.channel_rot = st.channel_rot;
+    sd.mean = d + o_mean[s]; sd.mean_quat = st.has_orientation ? d + o_q[s] : nullptr;
+    sd.step = reinterpret_cast<const long long*>(d + o_step[s]);
+    for (int a = 0; a < st.m; a++) sd.sigma[a] = st.sigma[a];
+    for (int a = 0; a < 3; a++) sd.sigma_rot[a] = st.sigma_rot[a];
+    sd.z = z_out[s]; sd.quat = st.has_orientation ? quat_out[s] : nullptr; sd.rows = st.rows;
+    const dim3 grid(gx, (unsigned)st.rows);
+    if (syn->mode == 0) rbisk::synth_stream_kernel<0><<<grid, 256, 0, stream>>>(sd, N, syn->seed, syn->first_filter);
+    else rbisk::synth_stream_kernel<1><<<grid, 256, 0, stream>>>(sd, N, syn->seed, syn->first_filter);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  return 0;
+}
+
+int rbis_batch_synthesize(rbis_batch_t* h, const rbis_synth_t* syn, double* imu_out, double* const* z_out, double* const* quat_out) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (int rc = use_device(h)) return rc;
+  if (int rc = main_stream_work(h)) return rc;
+  return synthesize_into(h, syn, imu_out, z_out, quat_out, h->stream);
+}
+
+int rbis_batch_run_fused_synth(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, int n_streams, const rbis_stream_t* streams,
+                               const rbis_synth_t* syn) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!syn) return fail(RBIS_ERR_INVALID, "syn is NULL");
+  if (n_streams > 0 && !streams) return fail(RBIS_ERR_INVALID, "streams is NULL");
+  return launch_fused(h, n_ops, ops, nullptr, 0, n_streams, streams, RBIS_MEM_DEVICE, true, false, syn);
 }
 
 int rbis_batch_ins_step(rbis_batch_t* h, const double* gyro, const double* accel, double dt, int64_t utime, int mem) {

@@ -1,0 +1,114 @@
+"""On-device synthesis of the per-filter sensor streams (rbis_batch_synthesize / rbis_batch_run_fused_synth).
+
+mode 0 is the splitmix64 -> Box-Muller generator of pronto_b200/synth.py:normal: the counters and the hash are integers (bit
+exact), the three libm calls differ from numpy's by an ulp or two.  A fused run over synthesised inputs must equal, bit for
+bit, a fused run over the same rows materialised with rbis_batch_synthesize -- which is also how the CPU oracle is fed
+exactly what the device drew."""
+import os
+
+import numpy as np
+import pytest
+
+from pronto_b200 import MeasStream, RBISBatch, SynthSpec, synth
+from pronto_b200.parity import max_errors
+
+from common import nominal_q, oracle_streams, scenario
+
+pytestmark = pytest.mark.gpu
+NTHREADS = min(16, os.cpu_count() or 1)
+
+
+def _spec(truth, k0, T, mode=0, first_filter=0, **kw):
+    d = synth.synth_spec_inputs(truth, k0, T)
+    return SynthSpec(synth.SEED, d["imu_mean"], d["imu_step"], d["streams"], mode=mode, first_filter=first_filter, **kw)
+
+
+def _streams(st):
+    return [MeasStream(synth.LEGODO_IDX, None, st["R_legodo"]), MeasStream(synth.POSE_IDX, None, st["R_pose"], quat=True)]
+
+
+def test_exact_mode_reproduces_the_numpy_generator():
+    N, T = 700, 230
+    sc = scenario(N, T)
+    st = sc["st"]
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        got = b.synthesize(_spec(sc["truth"], 0, T))
+    for name, g, ref in (("imu", got["imu"], st["imu"]), ("legodo", got["z"][0], st["legodo"]), ("pose_z", got["z"][1], st["pose_z"]),
+                         ("pose_q", got["quat"][1], st["pose_q"])):
+        g = g.cpu().numpy()
+        assert g.shape == ref.shape, name
+        assert np.max(np.abs(g - ref)) <= 2e-13 * max(1.0, np.max(np.abs(ref))), (name, np.max(np.abs(g - ref)))
+    # explicit sigmas instead of sqrt(q / dt) give the same rows
+    p = synth.NOMINAL
+    with RBISBatch(N) as b:
+        again = b.synthesize(_spec(sc["truth"], 0, T, sigma_gyro=np.sqrt(p["q_gyro"] / p["dt"]), sigma_accel=np.sqrt(p["q_accel"] / p["dt"])))
+    assert np.max(np.abs(again["imu"].cpu().numpy() - got["imu"].cpu().numpy())) < 1e-15
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_run_over_synthesised_inputs_equals_run_over_materialised_rows(oracle, mode):
+    N, T = 300, 220
+    sc = scenario(N, T, tumbling=True)
+    st = sc["st"]
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        spec = _spec(sc["truth"], 0, T, mode=mode)
+        b.run_fused_synth(st["events"], _streams(st), spec)
+        a = b.get_state()
+        rows = b.synthesize(spec)
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused(st["events"], imu=rows["imu"], streams=[MeasStream(synth.LEGODO_IDX, rows["z"][0], st["R_legodo"]),
+                                                            MeasStream(synth.POSE_IDX, rows["z"][1], st["R_pose"], quat=rows["quat"][1])])
+        c = b.get_state()
+    for x, y in zip(a[:4], c[:4]):
+        assert np.array_equal(x, y)
+    # ... and the CPU oracle fed with what the device drew agrees to the per-step gate
+    orc = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), rows["imu"].cpu().numpy(),
+                              [dict(idx=synth.LEGODO_IDX, z=rows["z"][0].cpu().numpy(), R=st["R_legodo"]),
+                               dict(idx=synth.POSE_IDX, z=rows["z"][1].cpu().numpy(), R=st["R_pose"], quat=rows["quat"][1].cpu().numpy())],
+                              st["events"], n_threads=NTHREADS)
+    e = max_errors(a[0], a[1], a[2], orc["vec"], orc["quat"], orc["cov"])
+    assert max(e.values()) < 1e-9, e
+    if mode == 1:  # the fast generator draws unit-variance noise too
+        nz = (rows["z"][0].cpu().numpy() - sc["truth"]["v"][::2][:, :, None]) / synth.NOMINAL["r_vxyz"]
+        assert abs(nz.std() - 1.0) < 0.02 and abs(nz.mean()) < 0.02 and np.abs(nz).max() < 6.0
+
+
+def test_shards_draw_the_noise_of_their_global_filter_indices():
+    N, T = 512, 60
+    sc = scenario(N, T)
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        whole = b.synthesize(_spec(sc["truth"], 0, T, mode=1))["imu"].cpu().numpy()
+    for lo in (0, 256):
+        with RBISBatch(256) as b:
+            b.set_process_noise(*nominal_q())
+            part = b.synthesize(_spec(sc["truth"], 0, T, mode=1, first_filter=lo))["imu"].cpu().numpy()
+        assert np.array_equal(part, whole[:, :, lo:lo + 256])
+
+
+def test_consecutive_synth_launches_overlap_safely():
+    """Chunk after chunk through the double-buffered staging slots (with launch groups): same bits as one long program."""
+    N, T, CH = 4000, 120, 40
+    sc = scenario(N, T)
+    st = sc["st"]
+    ev = st["events"]
+    out = []
+    for groups in (1, 4):
+        with RBISBatch(N, launch_groups=groups, mapping=1) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            for k0 in range(0, T, CH):
+                sub = synth.make_streams(sc["truth"], 1, k0, CH)  # chunk-relative rows of the schedule
+                b.run_fused_synth(sub["events"], _streams(st), _spec(sc["truth"], k0, CH, mode=1))
+            out.append(b.get_state())
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(sc["vec"], sc["quat"], sc["cov"])
+        b.run_fused_synth(ev, _streams(st), _spec(sc["truth"], 0, T, mode=1))
+        out.append(b.get_state())
+    for o in out[1:]:
+        for x, y in zip(out[0][:4], o[:4]):
+            assert np.array_equal(x, y)

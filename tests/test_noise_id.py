@@ -41,6 +41,25 @@ def test_oracle_noise_id_matches_numpy_restatement():
     assert ref == 0.0 and len(errs) == 0
 
 
+def test_oracle_noise_id_matches_the_reference_compiled():
+    """oracle restatement == the reference's own state-estimator/src/noise_id/noise_id.cpp (sampleProcessForward,
+    negLogLikelihood) compiled unmodified into oracle/_ref: per-window errors and the likelihood."""
+    from oracle import oracle_api
+
+    if oracle_api.build_ref() is None:
+        pytest.skip("oracle/_ref/librbis_ref.so is not built and /root/reference is not mounted")
+    vec, quat, cov = filter_history(45)
+    q = nominal_q()
+    for (qg, qa, nw) in ((q[0], q[1], 10), (3 * q[0], 0.5 * q[1], 7), (q[0], q[1], 44), (q[0], q[1], 100)):
+        got, errs = oracle_api.noise_id_neg_loglik(vec, quat, cov, 1e-3, qg, qa, nw)
+        with oracle_api.reference():
+            ref, errs_ref = oracle_api.noise_id_neg_loglik(vec, quat, cov, 1e-3, qg, qa, nw)
+        assert len(errs) == len(errs_ref)
+        assert abs(ref - got) <= 1e-10 * max(1.0, abs(ref)), (ref, got)
+        if len(errs):
+            assert np.max(np.abs(errs - errs_ref)) < 1e-12
+
+
 def test_oracle_noise_id_prefers_the_generating_noise_level():
     """Sanity of the restated likelihood convention: rolling forward NOISE-FREE inputs, the error is tiny, so the
     likelihood must prefer smaller process noise (log det term dominates)."""
