@@ -613,9 +613,14 @@ def run_b200(args):
     leg("dense_variant", dense_leg, when=(variant & 2) != 0 and world == 1)
 
     # ---- e2e: host (pinned) inputs through the C ABI, results read back every launch ----
+    # Reading a result after every call keeps consecutive CALLS from overlapping, so these legs run on a handle whose calls are
+    # cut into pieces of ~100 ops (rbis_batch_config_t::piece_ops): the partially filled last wave of one piece overlaps the next.
     e2e = None
     n_local = (N + CHUNK - 1) // CHUNK
     if not args.no_e2e:
+        b.close()
+        b = new_batch(N, dense_only=args.dense_only, piece_ops=100)
+        stream = torch.cuda.ExternalStream(b.cuda_stream, device=dev)
         E = max(1, min(args.e2e_steps, K * L))
         ring = min(3, resident)
         host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in wl.chunks[c].items()} for c in range(ring)]

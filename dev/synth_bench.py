@@ -69,3 +69,36 @@ with RBISBatch(N) as b:
         b.record(); e1.record(stream)
         b.synchronize(); torch.cuda.synchronize()
         print(f"run_fused (resident inputs) x {K}: {e0.elapsed_time(e1) / K:.3f} ms per call on the device, host enqueue {1e3 * (t1 - t0) / K:.3f} ms per call")
+
+# ---- the bench's e2e_synth loop: one launch + statistics read-back per step, host one step ahead ----
+from pronto_b200 import capi
+with RBISBatch(N) as b:
+    b.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
+    b.set_state(vec0, quat0, cov0)
+    stream = torch.cuda.ExternalStream(b.cuda_stream, device=dev)
+    tv, tq = synth.truth_state_at(truth, K * Tc - 1)
+    n_local = (N + 1023) // 1024
+    res = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+    for variant in ("synth+stats+wait", "synth+wait", "synth+stats, sync at end"):
+        for rep in range(2):
+            b.set_state(vec0, quat0, cov0); b.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            tick = None
+            t_enq = t_wait = 0.0
+            for c in range(K):
+                t0 = time.perf_counter()
+                b.run_fused_synth(progs[c], sst, specs[c])
+                if "stats" in variant:
+                    b.stats_enqueue(tv, tq, res[c % 2], chunk=1024)
+                t = b.record()
+                t1 = time.perf_counter()
+                if "wait" in variant and tick is not None:
+                    b.wait(tick)
+                t2 = time.perf_counter()
+                tick = t
+                t_enq += t1 - t0; t_wait += t2 - t1
+            b.wait(tick)
+            e1.record(stream)
+            b.synchronize(); torch.cuda.synchronize()
+        print(f"{variant}: {e0.elapsed_time(e1) / K:.3f} ms per step; host enqueue {1e3 * t_enq / K:.3f} ms, host wait {1e3 * t_wait / K:.3f} ms per step")

@@ -102,6 +102,12 @@ typedef struct {
   int32_t lane_filters_per_cta; /* filters per CTA of the decoupled lane-per-filter kernels: 384 (three warps per scheduler, for
                               ensembles that fill the GPU), 256 or 128 (more SMs busy for 10-50 thousand filters); 0 = automatic.
                               Same bits for every value. */
+  int32_t piece_ops;       /* with launch groups, a fused program of >= 2 * piece_ops ops is cut into consecutive pieces of about
+                              this many ops over the same inputs, each piece one set of launches, so that the partially filled last
+                              wave of CTAs of a piece overlaps the next piece (rbis_batch.cu).  0 = automatic (256).  Smaller
+                              pieces (64-100) pay when the caller reads a result after every call, which keeps consecutive CALLS
+                              from overlapping; results do not depend on it. */
+  int32_t reserved;
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /

@@ -36,6 +36,8 @@ class Config(C.Structure):
         ("dense_only", C.c_int32),
         ("mapping", C.c_int32),
         ("lane_filters_per_cta", C.c_int32),
+        ("piece_ops", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -127,7 +127,7 @@ struct rbis_batch {
   // ---- launch groups: the ensemble's CTAs are split into n_groups contiguous ranges, each launched on its own
   // stream, so that consecutive fused launches overlap (group g of launch k+1 starts when group g of launch k
   // is done) and the partially filled last wave of a launch does not idle SMs.  n_groups == 1: plain path.
-  static constexpr int kMaxGroups = 8, kRing = 4;
+  static constexpr int kMaxGroups = 8, kRing = 8;
   int n_groups = 1;
   cudaStream_t gstream[kMaxGroups] = {};
   cudaStream_t upload_stream = nullptr;
@@ -505,16 +505,12 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   cudaStream_t cst = h->copy_stream;
   const bool staging = (mem == RBIS_MEM_HOST) || syn != nullptr;
   const bool grouped = h->n_groups > 1;
-  const int ring = (int)(h->launch_seq % rbis_batch::kRing);
   if (staging) {
     if (grouped && slot.ring >= 0) {
       for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(cst, h->gdone[slot.ring][g], 0));
     } else {
       CUDA_TRY(cudaStreamWaitEvent(cst, slot.consumed, 0));
     }
-  }
-  if (grouped && h->gdone_valid[ring]) {  // ring slot reuse: the launch that used it (4 launches ago) must be done
-    for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaEventSynchronize(h->gdone[ring][g]));
   }
   kp.imu_map = use_maps ? h->d_map[0] : nullptr;
   kp.imu_cols = kp.imu_map ? h->map_cols[0] : N;
@@ -550,6 +546,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   }
   std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * kRShared, 0.0);
   bool any_shared = false;
+  bool shared_r[RBIS_MAX_STREAMS] = {};
   bool needs_general = false;  // some chunk is not an aligned triple -> the kernel instantiations that contain meas1 / meas_block
   bool passive_index = false;  // some stream measures omega or a directly -> couplings become non-zero
   for (int s = 0; s < n_streams; s++) {
@@ -574,7 +571,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       for (int c = 0; c < d.n_chunks; c++)
         if (d.chunk_fast[c] == -1)
           if (int rc = decorrelate_block(in.R, in.m, d.chunk_start[c], d.chunk_len[c], rs + rbisk::RS_W, rs + rbisk::RS_D)) return rc;
-      d.R = (grouped ? h->d_rshared_ring[ring] : h->d_rshared) + (size_t)s * kRShared;
+      d.R = h->d_rshared + (size_t)s * kRShared;  // grouped launches: re-pointed into the piece's ring slot below
+      shared_r[s] = true;
       any_shared = true;
     } else {
       if (int rc = copy_in(h, slot.rdiag[s], in.R, (size_t)in.m * N, mem, cst, &d.R)) return rc;
@@ -624,50 +622,67 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     h->launches++;
     if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
   } else {
-    // ---- grouped launch: uploads on their own stream into this launch's ring slot, one kernel per group ----
-    if ((size_t)n_ops > h->d_ops_ring_cap[ring]) {
-      if (h->d_ops_ring[ring]) cudaFree(h->d_ops_ring[ring]);  // idle: its last user was synchronised above
-      h->d_ops_ring[ring] = nullptr;
-      h->d_ops_ring_cap[ring] = 0;
-      size_t cap = (size_t)n_ops * 2;
-      if (cap < 1024) cap = 1024;
-      CUDA_TRY(cudaMalloc(&h->d_ops_ring[ring], cap * sizeof(rbisk::Op)));
-      h->d_ops_ring_cap[ring] = cap;
-    }
-    if (int rc = upload_small(h, h->d_ops_ring[ring], kops.data(), (size_t)n_ops * sizeof(rbisk::Op), h->upload_stream)) return rc;
-    if (any_shared)
-      if (int rc = upload_small(h, h->d_rshared_ring[ring], rshared.data(), rshared.size() * sizeof(double), h->upload_stream)) return rc;
-    CUDA_TRY(cudaEventRecord(h->uploaded[ring], h->upload_stream));
-    kp.ops = h->d_ops_ring[ring];
-    const bool wait_main = h->stream_dirty;
-    if (wait_main) CUDA_TRY(cudaEventRecord(h->pre_evt, h->stream));
+    // ---- grouped launch: the program is cut into consecutive PIECES of ~piece_ops ops over the same (already staged)
+    // inputs; every piece is one kernel per launch group, uploads on their own stream into the piece's ring slot.  Group g
+    // of a piece starts when group g of the previous piece (or call) is done, so the partially filled last wave of CTAs of
+    // one piece runs beside the next piece instead of idling most SMs; the state round trip through HBM per piece is
+    // ~2 KB per filter, noise against a hundred ops of work.
+    const int64_t piece_ops = h->cfg.piece_ops > 0 ? h->cfg.piece_ops : 256;
+    const int64_t pieces = n_ops >= 2 * piece_ops ? (n_ops + piece_ops - 1) / piece_ops : 1;
     const unsigned per = (grid + (unsigned)h->n_groups - 1) / (unsigned)h->n_groups;
     // Group g of this launch may only run ahead of the other groups of the previous launch when both launches cut the
     // ensemble into the SAME filter ranges.  The ranges are per * (filters per CTA), and the filters per CTA differ between
     // kernel variants (256 dense, 384 decoupled, ...): after a change every group waits for ALL groups of the previous launch.
     const long long part = (long long)per * geom.fpc;
-    const bool repartitioned = h->last_ring >= 0 && h->groups_dirty && h->last_part != part;
-    for (int g = 0; g < h->n_groups; g++) {
-      const unsigned b0 = (unsigned)g * per, b1 = b0 + per < grid ? b0 + per : grid;
-      cudaStream_t gs = h->gstream[g];
-      if (repartitioned)
-        for (int g2 = 0; g2 < h->n_groups; g2++) CUDA_TRY(cudaStreamWaitEvent(gs, h->gdone[h->last_ring][g2], 0));
-      if (wait_main) CUDA_TRY(cudaStreamWaitEvent(gs, h->pre_evt, 0));
-      if (staging) CUDA_TRY(cudaStreamWaitEvent(gs, slot.copied, 0));
-      CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
-      if (b1 > b0) {
-        kp.block_offset = (int)b0;
-        CUDA_TRY(launch_variant(variant, geom, b1 - b0, gs, kp));
-        h->launches++;
+    for (int64_t pc = 0; pc < pieces; pc++) {
+      const int64_t o0 = n_ops * pc / pieces, o1 = n_ops * (pc + 1) / pieces, np = o1 - o0;
+      const int ring = (int)(h->launch_seq % rbis_batch::kRing);
+      if (h->gdone_valid[ring])   // ring slot reuse: the piece that used it (kRing pieces ago) must be done
+        for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaEventSynchronize(h->gdone[ring][g]));
+      if ((size_t)np > h->d_ops_ring_cap[ring]) {
+        if (h->d_ops_ring[ring]) cudaFree(h->d_ops_ring[ring]);  // idle: its last user was synchronised above
+        h->d_ops_ring[ring] = nullptr;
+        h->d_ops_ring_cap[ring] = 0;
+        size_t cap = (size_t)np * 2;
+        if (cap < 1024) cap = 1024;
+        CUDA_TRY(cudaMalloc(&h->d_ops_ring[ring], cap * sizeof(rbisk::Op)));
+        h->d_ops_ring_cap[ring] = cap;
       }
-      CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
+      if (int rc = upload_small(h, h->d_ops_ring[ring], kops.data() + o0, (size_t)np * sizeof(rbisk::Op), h->upload_stream)) return rc;
+      if (any_shared) {
+        if (int rc = upload_small(h, h->d_rshared_ring[ring], rshared.data(), rshared.size() * sizeof(double), h->upload_stream)) return rc;
+        for (int s2 = 0; s2 < n_streams; s2++)
+          if (shared_r[s2]) kp.streams[s2].R = h->d_rshared_ring[ring] + (size_t)s2 * kRShared;
+      }
+      CUDA_TRY(cudaEventRecord(h->uploaded[ring], h->upload_stream));
+      kp.ops = h->d_ops_ring[ring];
+      kp.n_ops = np;
+      const bool wait_main = h->stream_dirty;
+      if (wait_main) CUDA_TRY(cudaEventRecord(h->pre_evt, h->stream));
+      const bool repartitioned = h->last_ring >= 0 && h->groups_dirty && h->last_part != part;
+      for (int g = 0; g < h->n_groups; g++) {
+        const unsigned b0 = (unsigned)g * per, b1 = b0 + per < grid ? b0 + per : grid;
+        cudaStream_t gs = h->gstream[g];
+        if (repartitioned)
+          for (int g2 = 0; g2 < h->n_groups; g2++) CUDA_TRY(cudaStreamWaitEvent(gs, h->gdone[h->last_ring][g2], 0));
+        if (wait_main) CUDA_TRY(cudaStreamWaitEvent(gs, h->pre_evt, 0));
+        if (staging && pc == 0) CUDA_TRY(cudaStreamWaitEvent(gs, slot.copied, 0));
+        CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
+        if (b1 > b0) {
+          kp.block_offset = (int)b0;
+          CUDA_TRY(launch_variant(variant, geom, b1 - b0, gs, kp));
+          h->launches++;
+        }
+        CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
+      }
+      h->gdone_valid[ring] = true;
+      h->last_ring = ring;
+      h->last_part = part;
+      h->groups_dirty = true;
+      h->stream_dirty = false;
+      if (staging) slot.ring = ring;   // the LAST piece that reads the staging slot marks its consumption
+      if (pc + 1 < pieces) h->launch_seq++;
     }
-    h->gdone_valid[ring] = true;
-    h->last_ring = ring;
-    h->last_part = part;
-    h->groups_dirty = true;
-    h->stream_dirty = false;
-    if (staging) slot.ring = ring;
   }
   h->launch_seq++;
   h->snap_valid = snap_valid;
@@ -707,6 +722,7 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->dense_only = 0;
   cfg->mapping = 0;
   cfg->lane_filters_per_cta = 0;
+  cfg->piece_ops = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -720,6 +736,7 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
     return fail(RBIS_ERR_INVALID, "launch_groups must be in [0, %d]", rbis_batch::kMaxGroups);
   if (c.mapping != 0 && c.mapping != 1 && c.mapping != 2 && c.mapping != 4 && c.mapping != 8 && c.mapping != 16)
     return fail(RBIS_ERR_INVALID, "mapping must be 0 (automatic), 1, 2, 4, 8 or 16 lanes per filter");
+  if (c.piece_ops < 0 || (c.piece_ops > 0 && c.piece_ops < 8)) return fail(RBIS_ERR_INVALID, "piece_ops must be 0 (automatic) or >= 8");
   if (c.lane_filters_per_cta != 0 && c.lane_filters_per_cta != 384 && c.lane_filters_per_cta != 256 && c.lane_filters_per_cta != 128)
     return fail(RBIS_ERR_INVALID, "lane_filters_per_cta must be 0 (automatic), 384, 256 or 128");
   int ndev = 0;
@@ -1035,20 +1052,6 @@ int rbis_batch_set_column_map(rbis_batch_t* h, int which, const int32_t* map, in
 int rbis_batch_run_fused(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, const double* imu, int64_t imu_rows,
                          int n_streams, const rbis_stream_t* streams, int mem) {
   if (n_streams > 0 && !streams) return fail(RBIS_ERR_INVALID, "streams is NULL");
-  // A long program over device-resident inputs is cut into consecutive pieces (same arrays, absolute rows): with launch
-  // groups the pieces overlap like consecutive calls do, so the partially filled last wave of CTAs of one piece runs
-  // beside the next piece instead of idling most SMs for the whole program.  The state round trip through HBM per
-  // piece is ~150 MB per 65,536 filters, noise against a few hundred ops of work.
-  constexpr int64_t kPieceOps = 256;
-  if (h && h->n_groups > 1 && mem == RBIS_MEM_DEVICE && ops && n_ops >= 2 * kPieceOps) {
-    if (int rc = launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem, true, /*dry_run=*/true)) return rc;
-    const int64_t pieces = (n_ops + kPieceOps - 1) / kPieceOps;
-    for (int64_t k = 0; k < pieces; k++) {
-      const int64_t o0 = n_ops * k / pieces, o1 = n_ops * (k + 1) / pieces;
-      if (int rc = launch_fused(h, o1 - o0, ops + o0, imu, imu_rows, n_streams, streams, mem)) return rc;
-    }
-    return 0;
-  }
   return launch_fused(h, n_ops, ops, imu, imu_rows, n_streams, streams, mem);
 }
 
@@ -1228,7 +1231,7 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
   double tbuf[25];
   std::memcpy(tbuf, truth_vec, 21 * sizeof(double));
   std::memcpy(tbuf + 21, truth_quat, 4 * sizeof(double));
-  CUDA_TRY(cudaMemcpyAsync(d_truth, tbuf, sizeof(tbuf), cudaMemcpyHostToDevice, h->stream));  // pageable: staged before return
+  if (int rc = upload_small(h, d_truth, tbuf, sizeof(tbuf), h->stream)) return rc;  // pinned ring: the host does not wait for the stream
   rbisk::stats_kernel<<<(unsigned)nch, chunk, chunk * sizeof(double), h->stream>>>(
       h->vec, h->quat, h->P, h->loglik, d_truth, d_truth + 21, 0, (long long)N, nullptr, d_chunks);
   CUDA_TRY(cudaGetLastError());
@@ -1280,7 +1283,7 @@ int rbis_batch_stats_allreduce(rbis_batch_t* h, void* nccl_comm, const double* t
   double tbuf[25];
   std::memcpy(tbuf, truth_vec, 21 * sizeof(double));
   std::memcpy(tbuf + 21, truth_quat, 4 * sizeof(double));
-  CUDA_TRY(cudaMemcpyAsync(d_truth, tbuf, sizeof(tbuf), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = upload_small(h, d_truth, tbuf, sizeof(tbuf), h->stream)) return rc;
   // every slot of the table has exactly one non-zero contributor (the rank that owns the chunk): the SUM all-reduce is
   // exact in any order (x + 0 = x), SURVEY.md 8e
   CUDA_TRY(cudaMemsetAsync(d_table, 0, n_table * sizeof(double), h->stream));

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header(rbis_lib):
     from pronto_b200 import capi
 
     assert C.sizeof(capi.Op) == 32
-    assert C.sizeof(capi.Config) == 48
+    assert C.sizeof(capi.Config) == 56
     assert C.sizeof(capi.Stream) == 4 * 4 + 9 * 4 + 4 + 3 * 8 + 8
     cfg = capi.Config()
     rbis_lib.rbis_default_config(C.byref(cfg))

@@ -468,8 +468,8 @@ def test_launch_groups_do_not_change_results_and_keep_call_order(oracle):
     ev = st["events"]
     cuts = [0, len(ev) // 3, 2 * len(ev) // 3, len(ev)]
     outs = []
-    for groups in (1, 0, 8):
-        with RBISBatch(N, launch_groups=groups) as b:
+    for groups, piece in ((1, 0), (0, 0), (8, 0), (6, 8)):   # the last: every call cut into pieces of ~8 ops (host inputs staged once)
+        with RBISBatch(N, launch_groups=groups, piece_ops=piece) as b:
             b.set_process_noise(*nominal_q())
             b.set_state(vec, quat, cov)
             mids = []
@@ -483,11 +483,11 @@ def test_launch_groups_do_not_change_results_and_keep_call_order(oracle):
                     q = nominal_q()
                     b.set_process_noise(q[0] * 1.5, q[1], q[2], q[3])  # write between launches
             outs.append((b.get_state(), mids[0]))
-    (g1, m1), (g0, m0), (g8, m8) = outs
-    for a, c in ((g1, g0), (g1, g8)):
+    (g1, m1), (g0, m0), (g8, m8), (gp, mp) = outs
+    for a, c in ((g1, g0), (g1, g8), (g1, gp)):
         for x, y in zip(a[:4], c[:4]):
             assert np.array_equal(x, y)
-    assert np.array_equal(m1, m0) and np.array_equal(m1, m8)
+    assert np.array_equal(m1, m0) and np.array_equal(m1, m8) and np.array_equal(m1, mp)
     # and the replicated filters agree with the oracle on the first 64
     ref = oracle.run_ensemble(sc["vec"], sc["quat"], sc["cov"], None, 0, nominal_q(), st["imu"], oracle_streams(st),
                               ev[:cuts[2]], n_threads=NTHREADS)

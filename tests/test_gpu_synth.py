@@ -96,8 +96,8 @@ def test_consecutive_synth_launches_overlap_safely():
     st = sc["st"]
     ev = st["events"]
     out = []
-    for groups in (1, 4):
-        with RBISBatch(N, launch_groups=groups, mapping=1) as b:
+    for groups, piece in ((1, 0), (4, 0), (4, 16)):
+        with RBISBatch(N, launch_groups=groups, mapping=1, piece_ops=piece) as b:
             b.set_process_noise(*nominal_q())
             b.set_state(sc["vec"], sc["quat"], sc["cov"])
             for k0 in range(0, T, CH):
