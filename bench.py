@@ -115,6 +115,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the informational legs (other configs, dense variant, next rows)")
+    ap.add_argument("--only-legs", default="", help="comma-separated leg names to run (others are skipped); for profiling one leg")
     ap.add_argument("--launch-groups", type=int, default=0, help="0 = library default (automatic)")
     ap.add_argument("--mapping", type=int, default=0, help="lanes per filter (rbis_batch_config_t::mapping); 0 = automatic")
     ap.add_argument("--dense-only", action="store_true", help="force the dense kernel variant (rbis_batch_config_t::dense_only)")
@@ -567,7 +568,7 @@ def run_b200(args):
 
     def leg(name, fn, when=True):
         """Informational legs never take the headline down with them."""
-        if not when or args.no_legs:
+        if not when or args.no_legs or (args.only_legs and name not in args.only_legs.split(",")):
             return
         try:
             t0 = time.time()
