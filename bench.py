@@ -92,7 +92,7 @@ def variant_name(v):
     lanes = v >> 4
     base = "decoupled (15x15 active block on chip; chosen at run time because every filter's omega / a covariance couplings are exactly zero, bit-identical to dense)" if v & 2 else "dense (whole 21x21 covariance on chip)"
     mapping = f"warp-group kernel, {lanes} lanes per filter" if lanes else "lane-per-filter kernel"
-    return f"{base}; {mapping}" + ("; with one-row / correlated-block paths" if v & 1 else "")
+    return f"{base}; {mapping}" + ("; with one-row / correlated-block paths" if v & 1 else "") + ("; SYN instantiation (input rows drawn in the kernel)" if v & 4 else "")
 
 
 def log(*a):
@@ -613,8 +613,9 @@ def run_b200(args):
 
     leg("dense_variant", dense_leg, when=(variant & 2) != 0 and world == 1)
 
-    # ---- e2e: host (pinned) inputs through the C ABI, results read back every launch ----
-    # Reading a result after every call keeps consecutive CALLS from overlapping, so these legs run on a handle whose calls are
+    # ---- e2e: host (pinned) inputs through the C ABI; one step = the headline's step (L fused launches, each with its own
+    # host->device input copy) followed by the read-back of the step's statistics on the host ----
+    # Reading a result keeps the calls on either side of it from overlapping, so these legs run on a handle whose calls are
     # cut into pieces of ~100 ops (rbis_batch_config_t::piece_ops): the partially filled last wave of one piece overlaps the next.
     e2e = None
     n_local = (N + CHUNK - 1) // CHUNK
@@ -635,7 +636,8 @@ def run_b200(args):
         b.set_state(wl.vec0, wl.quat0, wl.cov0)
 
         def e2e_step(i):
-            b.run_prepared(hprep[i % ring])
+            for j in range(L):
+                b.run_prepared(hprep[(i * L + j) % ring])
             b.stats_enqueue(tv, tq, resnp[i % 2], chunk=CHUNK)
             return b.record()
 
@@ -665,9 +667,10 @@ def run_b200(args):
         b.synchronize()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1))
         assert acc == E * min(CHUNK, N)
-        e2e = {"value": n_total * Tc * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.in_bytes + wl.progs[0].nbytes,
+        e2e = {"value": n_total * Tc * L * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": L * (wl.in_bytes + wl.progs[0].nbytes),
                "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": e2e_ms / E,
-               "step": f"one fused launch ({Tc} trajectory steps of every filter) with its own host->device input copy",
+               "step": f"{L} fused launches ({Tc} trajectory steps of every filter each), every one with its own host->device input copy from pinned "
+                       "memory, then the statistics of the step read back on the host",
                "bound": "PCIe: per-filter input rows cross the bus", "launches_per_step": (b.launch_count - l0) / E}
         del host, hnp, hprep
 
@@ -677,7 +680,7 @@ def run_b200(args):
         E = max(2, min(args.e2e_steps, K * L))
         SEED = 0x5EED20261018
         specs = []
-        for c in range(E + 2):
+        for c in range((E + 2) * L):
             d = synth.synth_spec_inputs(wl.truth, (c % resident) * Tc, Tc)
             specs.append(SynthSpec(SEED, d["imu_mean"], d["imu_step"], d["streams"], mode=1, first_filter=lo))
         sstreams = [MeasStream(synth.LEGODO_IDX, None, R_lego), MeasStream(synth.POSE_IDX, None, R_pose, quat=True)]
@@ -685,13 +688,14 @@ def run_b200(args):
         res_s = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
 
         def synth_step(i):
-            b.run_fused_synth(wl.progs[i % resident], sstreams, specs[i])
+            for j in range(L):
+                b.run_fused_synth(wl.progs[(i * L + j) % resident], sstreams, specs[i * L + j])
             b.stats_enqueue(tv, tq, res_s[i % 2], chunk=CHUNK)
             return b.record()
 
         b.set_state(wl.vec0, wl.quat0, wl.cov0)
         tick = None
-        for i in range(2):
+        for i in range(E, E + 2):  # warm-up
             t = synth_step(i)
             if tick is not None:
                 b.wait(tick)
@@ -716,10 +720,12 @@ def run_b200(args):
         barrier()
         b.synchronize()
         syn_ms = max_over_ranks(s0.elapsed_time(s1))
-        e2e_synth = {"value": n_total * Tc * E / (syn_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": spec_bytes + wl.progs[0].nbytes,
+        e2e_synth = {"value": n_total * Tc * L * E / (syn_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": L * (spec_bytes + wl.progs[0].nbytes),
                      "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": syn_ms / E,
                      "launches_per_step": (b.launch_count - l0) / E, "generator": "splitmix64 counters -> Box-Muller, fast mode (rbis_synth_t::mode 1)",
-                     "what": "rbis_batch_run_fused_synth: the host sends the noise-free rows and a seed, per-filter noise is drawn on the device"}
+                     "kernel_variant": variant_name(b.last_kernel_variant),
+                     "what": f"rbis_batch_run_fused_synth, {L} calls per step + statistics read-back: the host sends the noise-free rows and a seed, the "
+                             "fused kernel draws every filter's noisy rows itself (SYN instantiation) -- no per-filter input exists in HBM"}
         # parity of THIS run on a slice: filters 0..63 of rank 0 replayed by the CPU oracle from the rows the device drew
         if rank == 0:
             try:
@@ -735,7 +741,7 @@ def run_b200(args):
                 rv = wl.vec0[:, :S].cpu().numpy().copy(); rq = wl.quat0[:, :S].cpu().numpy().copy(); rP = wl.cov0[:, :S].cpu().numpy().copy()
                 rll, ut = np.zeros(S), 0
                 with new_batch(S) as bs:
-                    for i in range(E):
+                    for i in range(E * L):
                         d = synth.synth_spec_inputs(wl.truth, (i % resident) * Tc, Tc)
                         rows = bs.synthesize(SynthSpec(SEED, d["imu_mean"], d["imu_step"], d["streams"], mode=1, first_filter=lo))
                         ev = [(int(o["kind"]), int(o["stream"]), int(o["row"]), int(o["utime"]), float(o["dt"])) for o in wl.progs[i % resident]]
@@ -745,9 +751,9 @@ def run_b200(args):
                                                       ev, n_threads=os.cpu_count() or 1)
                         rv, rq, rP, rll, ut = ref["vec"], ref["quat"], ref["cov"], ref["loglik"], ev[-1][3]
                 err = max_errors(gv[:, :S].cpu().numpy(), gq[:, :S].cpu().numpy(), gc_[:, :S].cpu().numpy(), rv, rq, rP)
-                e2e_synth["parity_slice"] = {"filters": S, "steps": E * Tc, "max_err_vs_cpu_oracle": err, "gate": 1e-6,
+                e2e_synth["parity_slice"] = {"filters": S, "steps": E * L * Tc, "max_err_vs_cpu_oracle": err, "gate": 1e-6,
                                              "ok": bool(max(err.values()) < 1e-6)}
-                log(f"[rank 0] e2e_synth parity slice ({S} filters x {E * Tc} steps) vs CPU oracle: {err}")
+                log(f"[rank 0] e2e_synth parity slice ({S} filters x {E * L * Tc} steps) vs CPU oracle: {err}")
             except Exception as e:  # noqa: BLE001
                 e2e_synth["parity_slice"] = {"error": f"{type(e).__name__}: {e}"}
 

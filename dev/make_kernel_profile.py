@@ -32,7 +32,8 @@ def main():
     hdr = rows[0]
     r = rows[2 + li]
     g = lambda name: float(r[hdr.index(name)].replace(",", ""))
-    unit = lambda name: rows[1][hdr.index(name)]
+    units = rows[1]
+    unit = lambda name: units[hdr.index(name)]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     dram = g("dram__bytes_read.sum") * scale[unit("dram__bytes_read.sum")] + g("dram__bytes_write.sum") * scale[unit("dram__bytes_write.sum")]
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout

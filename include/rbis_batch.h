@@ -107,7 +107,10 @@ typedef struct {
                               wave of CTAs of a piece overlaps the next piece (rbis_batch.cu).  0 = automatic (256).  Smaller
                               pieces (64-100) pay when the caller reads a result after every call, which keeps consecutive CALLS
                               from overlapping; results do not depend on it. */
-  int32_t reserved;
+  int32_t synth_materialize; /* rbis_batch_run_fused_synth: 0 (default) = decoupled programs with the fast generator (rbis_synth_t::mode 1)
+                              draw their input rows INSIDE the fused kernel -- no per-filter input exists in HBM; 1 = always generate
+                              the rows into device buffers first and run the ordinary fused kernels over them.  Same bits either way
+                              (tests/test_gpu_synth.py). */
 } rbis_batch_config_t;
 
 /* One measurement stream = the constant part of an RBISIndexedMeasurement /
@@ -151,8 +154,9 @@ void* rbis_batch_stream(rbis_batch_t* h);
 int64_t rbis_batch_launch_count(const rbis_batch_t* h);
 /* Kernel variant the last rbis_batch_run_fused / single-op call launched: 0 dense, 2 decoupled (see
  * rbis_batch_config_t::dense_only), +1 when the program has measurement chunks other than uncorrelated aligned index
- * triples (the instantiations that also contain the one-row and the correlated-block updates), + 16 * lanes per filter
- * for the warp-group kernels (rbis_batch_config_t::mapping > 1); -1 before the first launch. */
+ * triples (the instantiations that also contain the one-row and the correlated-block updates), +4 when the kernel drew its
+ * input rows itself (rbis_batch_run_fused_synth, SYN instantiations), + 16 * lanes per filter for the warp-group kernels
+ * (rbis_batch_config_t::mapping > 1); -1 before the first launch. */
 int rbis_batch_last_kernel_variant(const rbis_batch_t* h);
 
 /* ---- RBISResetUpdate::updateFilter (MSE/rbis_update_interface.cpp:23-28): posterior := given,
@@ -227,7 +231,8 @@ typedef struct {
 typedef struct {
   uint64_t seed;
   int64_t first_filter;           /* global index of the handle's filter 0: shards of one ensemble draw the same noise for any GPU count */
-  int32_t mode;                   /* 0 exact, 1 fast */
+  int32_t mode;                   /* 0 exact (double precision, one hash pair per sample: pronto_b200/synth.py:normal), 1 fast (one hash per
+                                     PAIR of channels, single-precision Box-Muller; the mode the fused kernels can draw in-kernel) */
   int32_t n_streams;
   const double* imu_mean;         /* HOST [imu_rows][6]: noise-free gyro xyz, accelerometer xyz readings */
   const int64_t* imu_step;        /* HOST [imu_rows] */
@@ -242,8 +247,11 @@ typedef struct {
  * test feeds the CPU oracle exactly what the device drew. */
 int rbis_batch_synthesize(rbis_batch_t* h, const rbis_synth_t* syn, double* imu_out, double* const* z_out, double* const* quat_out);
 /* rbis_batch_run_fused with synthesised inputs: streams[s].z / .quat / .rows are ignored (taken from syn->streams[s]; a per-filter R
- * is a DEVICE array on this path), the rows are generated into library-owned device buffers (double buffered across calls) and consumed by the
- * fused launch.  Host -> device traffic per call: the op list and the noise-free rows. */
+ * is a DEVICE array on this path).  Mode 1 on a decoupled ensemble (rbis_batch_config_t::dense_only): the fused kernel draws every row
+ * it consumes itself, from the noise-free row and the filter's counters -- nothing is materialised, the launch reads no per-filter input.
+ * Otherwise (mode 0, dense kernels, rbis_batch_config_t::synth_materialize) the rows are generated into library-owned device buffers
+ * (double buffered across calls) and consumed by the ordinary fused launch; both ways give the same bits as rbis_batch_synthesize +
+ * rbis_batch_run_fused.  Host -> device traffic per call: the op list and the noise-free rows. */
 int rbis_batch_run_fused_synth(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* ops, int n_streams, const rbis_stream_t* streams,
                                const rbis_synth_t* syn);
 

@@ -117,7 +117,8 @@ class RBISBatch:
     """An ensemble of N RBIS filters on one GPU (rbis_batch_t)."""
 
     def __init__(self, n_filters, device=0, g_val=9.8, chi_tol=1e-6, ctor_folds_chi=True, renormalize_quat=False,
-                 snapshot_slots=0, launch_groups=0, dense_only=False, mapping=0, lane_filters_per_cta=0, piece_ops=0):
+                 snapshot_slots=0, launch_groups=0, dense_only=False, mapping=0, lane_filters_per_cta=0, piece_ops=0,
+                 synth_materialize=False):
         self.lib = capi.load()
         cfg = capi.Config()
         self.lib.rbis_default_config(C.byref(cfg))
@@ -128,6 +129,7 @@ class RBISBatch:
         cfg.dense_only = int(bool(dense_only))
         cfg.lane_filters_per_cta = int(lane_filters_per_cta)
         cfg.piece_ops = int(piece_ops)
+        cfg.synth_materialize = int(bool(synth_materialize))
         cfg.mapping = int(mapping)  # lanes per filter: 0 automatic, 1 lane-per-filter kernels, 2/4/8/16 warp-group kernels
         self.h = C.c_void_p()
         capi.check(self.lib.rbis_batch_create(C.byref(self.h), int(n_filters), C.byref(cfg)))

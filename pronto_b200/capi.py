@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("mapping", C.c_int32),
         ("lane_filters_per_cta", C.c_int32),
         ("piece_ops", C.c_int32),
-        ("reserved", C.c_int32),
+        ("synth_materialize", C.c_int32),
     ]
 
 

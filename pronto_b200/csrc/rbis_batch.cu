@@ -106,7 +106,7 @@ struct rbis_batch {
   double* d_notch_state = nullptr;  // [3][MAX_NOTCH][4][notch_cols]
   int64_t notch_cols = 0;
   DevBuf notch_stage;               // device copy of a host chunk
-  int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block, bits 4.. lanes per filter (0 = one)
+  int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block, bit 2 SYN (rows drawn in the kernel), bits 4.. lanes per filter (0 = one)
   int mapping = 1;        // lanes per filter of the fused kernels: 1 = lane-per-filter kernels, 2/4/8/16 = warp-group kernels
   int lane_tpb = 384;     // filters per CTA of the decoupled lane-per-filter kernels (384, 256, 128)
   int n_sms = 148;
@@ -144,6 +144,8 @@ struct rbis_batch {
   char* pin_base = nullptr;
   cudaEvent_t pin_evt[kPinSlots] = {};
   int pin_next = 0;
+  DevBuf d_syn;                 // noise-free rows of a fused-synthesis launch (plain path)
+  DevBuf d_syn_ring[kRing];     // ... and per ring slot (grouped launches)
   rbisk::Op* d_ops_ring[kRing] = {};
   size_t d_ops_ring_cap[kRing] = {};
   double* d_rshared_ring[kRing] = {};
@@ -213,8 +215,9 @@ LaunchGeom launch_geom(int variant, int mapping, int lane_tpb, long long N, int 
   return g;
 }
 
-cudaError_t launch_variant(int variant, const LaunchGeom& g, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
-  if (g.tu) return g.tu->launch(variant & 1, (variant & 2) ? 1 : 0, blocks, g.threads, g.smem, st, &kp);
+cudaError_t launch_variant(int variant, int syn, const LaunchGeom& g, unsigned blocks, cudaStream_t st, const rbisk::KParams& kp) {
+  if (g.tu) return g.tu->launch(variant & 1, (variant & 2) ? 1 : 0, syn, blocks, g.threads, g.smem, st, &kp);
+  if (syn) return cudaErrorInvalidValue;  // the dense lane-per-filter kernels have no SYN instantiation
   if (variant & 1) rbisk::rbis_fused_kernel<true><<<blocks, g.threads, g.smem, st>>>(kp);
   else rbisk::rbis_fused_kernel<false><<<blocks, g.threads, g.smem, st>>>(kp);
   return cudaGetLastError();
@@ -499,27 +502,125 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   kp.g_val = h->cfg.g_val; kp.chi_tol = h->cfg.chi_tol;
   kp.ctor_folds_chi = h->cfg.ctor_folds_chi; kp.renorm = h->cfg.renormalize_quat;
 
+  // ---- measurement streams: index sets, chunks, kernel variant (no data movement yet) ----
+  kp.imu_map = use_maps ? h->d_map[0] : nullptr;
+  kp.imu_cols = kp.imu_map ? h->map_cols[0] : N;
+  std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * kRShared, 0.0);
+  bool any_shared = false;
+  bool shared_r[RBIS_MAX_STREAMS] = {};
+  bool needs_general = false;  // some chunk is not an aligned triple -> the kernel instantiations that contain meas1 / meas_block
+  bool passive_index = false;  // some stream measures omega or a directly -> couplings become non-zero
+  for (int s = 0; s < n_streams; s++) {
+    const rbis_stream_t& in = streams[s];
+    rbisk::StreamDesc& d = kp.streams[s];
+    if (int rc = validate_stream(s, in)) return rc;
+    d.m = in.m; d.has_orient = in.has_orientation ? 1 : 0; d.r_mode = in.r_mode;
+    for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
+    d.map = use_maps ? h->d_map[1 + s] : nullptr;
+    d.cols = d.map ? h->map_cols[1 + s] : N;
+    if (in.rows == 0) { d.n_chunks = 0; continue; }
+    plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
+    mark_fast_chunks(d, &needs_general);
+    for (int a = 0; a < in.m; a++)
+      if (!rbisk::is_act(in.idx[a])) passive_index = true;
+    if (in.r_mode == RBIS_R_SHARED_FULL) {
+      double* rs = &rshared[(size_t)s * kRShared];
+      std::memcpy(rs, in.R, sizeof(double) * in.m * in.m);
+      for (int c = 0; c < d.n_chunks; c++)
+        if (d.chunk_fast[c] == -1)
+          if (int rc = decorrelate_block(in.R, in.m, d.chunk_start[c], d.chunk_len[c], rs + rbisk::RS_W, rs + rbisk::RS_D)) return rc;
+      d.R = h->d_rshared + (size_t)s * kRShared;  // grouped launches: re-pointed into the piece's ring slot below
+      shared_r[s] = true;
+      any_shared = true;
+    }
+  }
+  // ---- kernel variant ----
+  int variant = needs_general ? 1 : 0;
+  const bool dc_eligible = !h->cfg.dense_only && !passive_index && restores_ok;
+  if (dc_eligible && h->decoupled < 0) {
+    // one device pass over the couplings, then a host read: happens once after set_state / set_filter, not per launch
+    if (int rc = main_stream_work(h)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    rbisk::coupling_check_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->P, (long long)N, h->d_flag);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->decoupled = flag ? 0 : 1;
+  }
+  if (dc_eligible && h->decoupled == 1) variant |= 2;
+  // Synthesised inputs: the decoupled kernels have SYN instantiations that draw the rows themselves (mode 1), so nothing is
+  // materialised and the launch reads no per-filter input; otherwise the rows are generated into the staging slot first.
+  const bool fuse_syn = syn != nullptr && syn->mode == 1 && !h->cfg.synth_materialize && (variant & 2) != 0 &&
+                        (h->mapping > 1 || !(variant & 1));
+  if (syn) {
+    if (kp.imu_map) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
+    for (int s = 0; s < n_streams; s++)
+      if (use_maps && h->d_map[1 + s]) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
+    if ((syn->sigma_gyro < 0 || syn->sigma_accel < 0) && !(syn->dt > 0)) return fail(RBIS_ERR_INVALID, "per-filter IMU noise needs dt > 0");
+  }
+  // the noise-free rows of a fused-synthesis launch as one host block: [imu_mean | imu_step | per stream: mean, mean_quat, step]
+  std::vector<double> syn_host;
+  size_t syn_o_imu = 0, syn_o_istep = 0, syn_o_mean[RBIS_MAX_STREAMS] = {}, syn_o_q[RBIS_MAX_STREAMS] = {}, syn_o_step[RBIS_MAX_STREAMS] = {};
+  if (fuse_syn) {
+    if (syn->imu_rows > 0 && (!syn->imu_mean || !syn->imu_step)) return fail(RBIS_ERR_INVALID, "bad synth IMU description");
+    size_t words = (size_t)syn->imu_rows * 7;
+    for (int s = 0; s < n_streams; s++) {
+      const rbis_synth_stream_t& ss = syn->streams[s];
+      if (ss.rows > 0 && (!ss.mean || !ss.step)) return fail(RBIS_ERR_INVALID, "synth stream %d: mean and step are required", s);
+      if (ss.has_orientation && ss.rows > 0 && !ss.mean_quat) return fail(RBIS_ERR_INVALID, "synth stream %d: mean_quat is required", s);
+      words += (size_t)ss.rows * (ss.m + 1 + (ss.has_orientation ? 4 : 0));
+    }
+    syn_host.resize(words + 1);
+    size_t off = 0;
+    auto put = [&](const void* src, size_t n_words) { if (n_words) std::memcpy(syn_host.data() + off, src, n_words * 8); off += n_words; return off - n_words; };
+    syn_o_imu = put(syn->imu_mean, (size_t)syn->imu_rows * 6);
+    syn_o_istep = put(syn->imu_step, (size_t)syn->imu_rows);
+    for (int s = 0; s < n_streams; s++) {
+      const rbis_synth_stream_t& ss = syn->streams[s];
+      syn_o_mean[s] = put(ss.mean, (size_t)ss.rows * ss.m);
+      if (ss.has_orientation) syn_o_q[s] = put(ss.mean_quat, (size_t)ss.rows * 4);
+      syn_o_step[s] = put(ss.step, (size_t)ss.rows);
+    }
+    kp.syn.seed = syn->seed; kp.syn.first_filter = syn->first_filter;
+    kp.syn.sigma_gyro = syn->sigma_gyro; kp.syn.sigma_accel = syn->sigma_accel; kp.syn.dt = syn->dt;
+    for (int s = 0; s < n_streams; s++) {
+      const rbis_synth_stream_t& ss = syn->streams[s];
+      rbisk::SynStreamK& k = kp.syn.st[s];
+      for (int a = 0; a < ss.m; a++) k.sigma[a] = ss.sigma[a];
+      for (int a = 0; a < 3; a++) k.sigma_rot[a] = ss.sigma_rot[a];
+      k.channel = ss.channel; k.channel_rot = ss.channel_rot;
+    }
+  }
+  // device addresses of that block once it has a home (d = base of the uploaded copy)
+  auto point_syn = [&](const double* d) {
+    kp.syn.imu_mean = d + syn_o_imu;
+    kp.syn.imu_step = reinterpret_cast<const long long*>(d + syn_o_istep);
+    for (int s = 0; s < n_streams; s++) {
+      rbisk::SynStreamK& k = kp.syn.st[s];
+      k.mean = d + syn_o_mean[s];
+      k.mean_quat = syn->streams[s].has_orientation ? d + syn_o_q[s] : nullptr;
+      k.step = reinterpret_cast<const long long*>(d + syn_o_step[s]);
+    }
+  };
+
   // ---- inputs: stage host arrays on the copy stream (double buffered), or use device arrays in place ----
   StagingSlot& slot = h->slots[h->slot_toggle];
-  h->slot_toggle ^= 1;
   cudaStream_t cst = h->copy_stream;
-  const bool staging = (mem == RBIS_MEM_HOST) || syn != nullptr;
+  const bool staging = ((mem == RBIS_MEM_HOST) || syn != nullptr) && !fuse_syn;
   const bool grouped = h->n_groups > 1;
   if (staging) {
+    h->slot_toggle ^= 1;
     if (grouped && slot.ring >= 0) {
       for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(cst, h->gdone[slot.ring][g], 0));
     } else {
       CUDA_TRY(cudaStreamWaitEvent(cst, slot.consumed, 0));
     }
   }
-  kp.imu_map = use_maps ? h->d_map[0] : nullptr;
-  kp.imu_cols = kp.imu_map ? h->map_cols[0] : N;
-  if (syn) {
+  if (syn && !fuse_syn) {
     // synthesise this call's rows into the staging slot, on the copy stream (ordered after everything the main stream has
     // enqueued so far: the process-noise arrays the IMU synthesis may read)
-    if (kp.imu_map) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
-    for (int s = 0; s < n_streams; s++)
-      if (use_maps && h->d_map[1 + s]) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
     double* z_out[RBIS_MAX_STREAMS] = {};
     double* q_out[RBIS_MAX_STREAMS] = {};
     if (imu_rows > 0 && slot.imu.ensure((size_t)imu_rows * 6 * (size_t)N)) return fail(RBIS_ERR_ALLOC, "synth IMU buffer allocation failed");
@@ -541,60 +642,23 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (int rc = synthesize_into(h, syn, slot.imu.p, z_out, q_out, cst)) return rc;
     imu = slot.imu.p;
   }
-  if (imu) {
+  if (imu && !fuse_syn) {
     if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * (size_t)kp.imu_cols, mem, cst, &kp.imu)) return rc;
   }
-  std::vector<double> rshared((size_t)RBIS_MAX_STREAMS * kRShared, 0.0);
-  bool any_shared = false;
-  bool shared_r[RBIS_MAX_STREAMS] = {};
-  bool needs_general = false;  // some chunk is not an aligned triple -> the kernel instantiations that contain meas1 / meas_block
-  bool passive_index = false;  // some stream measures omega or a directly -> couplings become non-zero
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
     rbisk::StreamDesc& d = kp.streams[s];
-    if (int rc = validate_stream(s, in)) return rc;
-    d.m = in.m; d.has_orient = in.has_orientation ? 1 : 0; d.r_mode = in.r_mode;
-    for (int a = 0; a < in.m; a++) d.idx[a] = in.idx[a];
-    d.map = use_maps ? h->d_map[1 + s] : nullptr;
-    d.cols = d.map ? h->map_cols[1 + s] : N;
-    if (in.rows == 0) { d.n_chunks = 0; continue; }
-    plan_chunks(in.m, in.r_mode, in.r_mode == RBIS_R_SHARED_FULL ? in.R : nullptr, d);
-    mark_fast_chunks(d, &needs_general);
-    for (int a = 0; a < in.m; a++)
-      if (!rbisk::is_act(in.idx[a])) passive_index = true;
-    if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, &d.z)) return rc;
-    if (in.has_orientation)
-      if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
-    if (in.r_mode == RBIS_R_SHARED_FULL) {
-      double* rs = &rshared[(size_t)s * kRShared];
-      std::memcpy(rs, in.R, sizeof(double) * in.m * in.m);
-      for (int c = 0; c < d.n_chunks; c++)
-        if (d.chunk_fast[c] == -1)
-          if (int rc = decorrelate_block(in.R, in.m, d.chunk_start[c], d.chunk_len[c], rs + rbisk::RS_W, rs + rbisk::RS_D)) return rc;
-      d.R = h->d_rshared + (size_t)s * kRShared;  // grouped launches: re-pointed into the piece's ring slot below
-      shared_r[s] = true;
-      any_shared = true;
-    } else {
+    if (in.rows == 0) continue;
+    if (!fuse_syn) {
+      if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, &d.z)) return rc;
+      if (in.has_orientation)
+        if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
+    }
+    if (in.r_mode != RBIS_R_SHARED_FULL) {
       if (int rc = copy_in(h, slot.rdiag[s], in.R, (size_t)in.m * N, mem, cst, &d.R)) return rc;
     }
   }
   if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
-  // ---- kernel variant ----
-  int variant = needs_general ? 1 : 0;
-  const bool dc_eligible = !h->cfg.dense_only && !passive_index && restores_ok;
-  if (dc_eligible && h->decoupled < 0) {
-    // one device pass over the couplings, then a host read: happens once after set_state / set_filter, not per launch
-    if (int rc = main_stream_work(h)) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
-    rbisk::coupling_check_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->P, (long long)N, h->d_flag);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    int flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->decoupled = flag ? 0 : 1;
-  }
-  if (dc_eligible && h->decoupled == 1) variant |= 2;
   const LaunchGeom geom = launch_geom(variant, h->mapping, h->lane_tpb, N, h->n_sms);
   const unsigned grid = geom.grid;
   if (!grouped) {
@@ -616,9 +680,17 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (int rc = upload_small(h, h->d_ops, kops.data(), (size_t)n_ops * sizeof(rbisk::Op), h->stream)) return rc;
     if (any_shared)
       if (int rc = upload_small(h, h->d_rshared, rshared.data(), rshared.size() * sizeof(double), h->stream)) return rc;
+    if (fuse_syn) {
+      if (h->d_syn.cap < syn_host.size()) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));  // an earlier launch may still read the old block
+        if (h->d_syn.ensure(syn_host.size() * 2)) return fail(RBIS_ERR_ALLOC, "synth row buffer allocation failed");
+      }
+      if (int rc = upload_small(h, h->d_syn.p, syn_host.data(), syn_host.size() * 8, h->stream)) return rc;
+      point_syn(h->d_syn.p);
+    }
     kp.ops = h->d_ops;
     kp.block_offset = 0;
-    CUDA_TRY(launch_variant(variant, geom, grid, h->stream, kp));
+    CUDA_TRY(launch_variant(variant, fuse_syn ? 1 : 0, geom, grid, h->stream, kp));
     h->launches++;
     if (staging) CUDA_TRY(cudaEventRecord(slot.consumed, h->stream));
   } else {
@@ -654,6 +726,13 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
         for (int s2 = 0; s2 < n_streams; s2++)
           if (shared_r[s2]) kp.streams[s2].R = h->d_rshared_ring[ring] + (size_t)s2 * kRShared;
       }
+      if (fuse_syn) {
+        // every piece carries its own copy of the noise-free rows: a ring slot is reused as soon as ITS piece is done
+        if (h->d_syn_ring[ring].cap < syn_host.size() && h->d_syn_ring[ring].ensure(syn_host.size() * 2))
+          return fail(RBIS_ERR_ALLOC, "synth row buffer allocation failed");
+        if (int rc = upload_small(h, h->d_syn_ring[ring].p, syn_host.data(), syn_host.size() * 8, h->upload_stream)) return rc;
+        point_syn(h->d_syn_ring[ring].p);
+      }
       CUDA_TRY(cudaEventRecord(h->uploaded[ring], h->upload_stream));
       kp.ops = h->d_ops_ring[ring];
       kp.n_ops = np;
@@ -670,7 +749,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
         CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
         if (b1 > b0) {
           kp.block_offset = (int)b0;
-          CUDA_TRY(launch_variant(variant, geom, b1 - b0, gs, kp));
+          CUDA_TRY(launch_variant(variant, fuse_syn ? 1 : 0, geom, b1 - b0, gs, kp));
           h->launches++;
         }
         CUDA_TRY(cudaEventRecord(h->gdone[ring][g], gs));
@@ -699,7 +778,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       if (f == 2) f = as_launch;
   }
   h->snap_dc = snap_dc;
-  h->last_variant = variant | (h->mapping > 1 ? (h->mapping << 4) : 0);
+  h->last_variant = variant | (fuse_syn ? 4 : 0) | (h->mapping > 1 ? (h->mapping << 4) : 0);
   h->utime = last_utime;
   return 0;
 }
@@ -723,6 +802,7 @@ void rbis_default_config(rbis_batch_config_t* cfg) {
   cfg->mapping = 0;
   cfg->lane_filters_per_cta = 0;
   cfg->piece_ops = 0;
+  cfg->synth_materialize = 0;
 }
 
 int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_config_t* cfg) {
@@ -864,7 +944,8 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   cudaFree(h->snap); cudaFree(h->d_ops); cudaFree(h->d_rshared); cudaFree(h->d_flag); cudaFree(h->d_notch_state);
   h->notch_stage.release();
   for (auto& m : h->d_map) cudaFree(m);
-  h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release(); h->synth_small.release();
+  h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release(); h->synth_small.release(); h->d_syn.release();
+  for (auto& b : h->d_syn_ring) b.release();
   for (auto& s : h->slots) {
     s.imu.release();
     for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }

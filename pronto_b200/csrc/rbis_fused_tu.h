@@ -13,7 +13,8 @@ struct rbis_fused_tu_t {
   size_t kparams_bytes;
   cudaError_t (*prepare)();
   // blocks_variant: the program has one-row / correlated chunks (lane-per-filter kernels: instantiation with those paths)
-  cudaError_t (*launch)(int blocks_variant, int decoupled, unsigned grid, int threads, int smem, cudaStream_t st, const void* kparams);
+  // syn: the SYN instantiation (input rows drawn inside the kernel, KParams::syn); decoupled kernels without blocks_variant only
+  cudaError_t (*launch)(int blocks_variant, int decoupled, int syn, unsigned grid, int threads, int smem, cudaStream_t st, const void* kparams);
 };
 extern "C" {
 extern const rbis_fused_tu_t rbis_fused_tu_dc384, rbis_fused_tu_dc256, rbis_fused_tu_dc128;

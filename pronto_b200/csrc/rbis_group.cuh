@@ -330,14 +330,13 @@ __device__ __forceinline__ void g_sweep(double* Pf, const Own<G, Geo<G, DC>::NA>
 
 // Aligned index triple I0..I0+2 (leg-odometry velocity, pose position / orientation, ...): rbis.cpp:124-143 with
 // S = L D L^T, Y = L^-1 P[idx,:], P -= Y^T D^-1 Y, x += Y^T D^-1 L^-1 r.  Same arithmetic as rbisk::meas3.
-template <int G, bool DC>
-__device__ __forceinline__ void g_meas3(double* Pf, const int l, FilterState& s, const StreamDesc& st, int a0, int I0,
+template <int G, bool DC, bool SYN>
+__device__ __forceinline__ void g_meas3(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int I0,
                                         long long row, long long N, long long n, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
   constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
   double z[3], Rdg[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) z[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * st.cols + sn);
+  src.z3(st, row, a0, sn, z);
   if (st.r_mode == 1) {
 #pragma unroll
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
@@ -404,12 +403,12 @@ __device__ __forceinline__ void g_meas3(double* Pf, const int l, FilterState& s,
 }
 
 // One-row chunk on state index idx (rbisk::meas1).
-template <int G, bool DC>
-__device__ __forceinline__ void g_meas1(double* Pf, const int l, FilterState& s, const StreamDesc& st, int a0, int idx,
+template <int G, bool DC, bool SYN>
+__device__ __forceinline__ void g_meas1(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int idx,
                                         long long row, long long N, long long n, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
   constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
-  const double z = ldg_early(st.z + (row * st.m + a0) * st.cols + sn);
+  const double z = src.z(st, row, a0, sn);
   const double Rv = (st.r_mode == 1) ? ldg_early(st.R + (long long)a0 * N + n) : __ldg(st.R + a0 + (long long)st.m * a0);
   const Own<G, NA> w(l);
   const int pi = pos_of<DC>(idx);
@@ -447,8 +446,8 @@ __device__ __forceinline__ void g_meas1(double* Pf, const int l, FilterState& s,
 
 // A chunk of M correlated rows, decorrelated by the host (rbisk::meas_block): M scalar updates with rows
 // H'_a = sum_{b<=a} w_ab H_b and noise D_a.
-template <int G, bool DC>
-__device__ __forceinline__ void g_meas_block(double* Pf, const int l, FilterState& s, const StreamDesc& st, int a0, int M,
+template <int G, bool DC, bool SYN>
+__device__ __forceinline__ void g_meas_block(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int M,
                                              long long row, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
   constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
@@ -487,7 +486,7 @@ __device__ __forceinline__ void g_meas_block(double* Pf, const int l, FilterStat
         const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
         rb = dq - (xi - c0);
       } else {
-        rb = __ldg(st.z + (row * st.m + (a0 + b)) * st.cols + sn) - xi;
+        rb = src.template z<false>(st, row, a0 + b, sn) - xi;
       }
       rp_ = fma(wt, rb, rp_);
     }
@@ -560,7 +559,8 @@ __device__ __forceinline__ void g_cov_store(const double* Pf, const int l, doubl
 // shared-memory addresses here, so the general paths cost the common program nothing).
 // MAXW = warps per CTA the launch may use (register budget: 8 -> 255 registers, 16 -> 128).
 // ------------------------------------------------------------------------------------------------
-template <int G, bool DC, int MAXW>
+// SYN = true: input rows drawn inside the kernel (KParams::syn), as in rbisk::rbis_fused_kernel.
+template <int G, bool DC, int MAXW, bool SYN = false>
 __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_constant__ KParams p) {
   using GE = Geo<G, DC>;
   constexpr int FPW = GE::FPW, S = GE::S;
@@ -600,6 +600,13 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
   // Ops are fetched two ahead, and the INPUT ROWS of the next op are prefetched into L1 while the current op runs: with
   // one or two warps per scheduler nothing else hides the latency of a first touch of HBM.
   auto prefetch = [&](const double* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
+  unsigned long long syn_kf = 0;
+  double syn_sg = 0.0, syn_sa = 0.0;
+  if constexpr (SYN) {
+    syn_kf = p.syn.seed ^ ((unsigned long long)(p.syn.first_filter + n) * SYN_K1);
+    syn_sg = p.syn.sigma_gyro >= 0 ? p.syn.sigma_gyro : sqrt(__ldg(p.q_gyro + n) / p.syn.dt);
+    syn_sa = p.syn.sigma_accel >= 0 ? p.syn.sigma_accel : sqrt(__ldg(p.q_accel + n) / p.syn.dt);
+  }
   auto prefetch_inputs = [&](const Op& o) {
     if (o.kind == 0) {
       const double* base = p.imu + o.row * 6 * p.imu_cols + imu_n;
@@ -623,13 +630,25 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
     const Op op = op1;
     op1 = op2;
     if (oi + 2 < p.n_ops) op2 = load_op(oi + 2);
-    if (oi + 1 < p.n_ops) prefetch_inputs(op1);
+    if constexpr (!SYN) {
+      if (oi + 1 < p.n_ops) prefetch_inputs(op1);
+    }
     if (op.kind == 0) {
       // ---- IMU process step: same linearisation / state code as the lane-per-filter kernel ----
       const double* base = p.imu + op.row * 6 * p.imu_cols + imu_n;
       const long long Ni = p.imu_cols;
-      const V3 gyro{ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
-      const V3 acc{ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
+      V3 gyro, acc;
+      if constexpr (SYN) {
+        const unsigned long long kfs = syn_kf ^ ((unsigned long long)__ldg(p.syn.imu_step + op.row) * SYN_K2);
+        const double* mu = p.syn.imu_mean + op.row * 6;
+        double nn[6];
+        syn_normals_k<1, 6>(kfs, 0u, nn);
+        gyro = {fma(syn_sg, nn[0], __ldg(mu)), fma(syn_sg, nn[1], __ldg(mu + 1)), fma(syn_sg, nn[2], __ldg(mu + 2))};
+        acc = {fma(syn_sa, nn[3], __ldg(mu + 3)), fma(syn_sa, nn[4], __ldg(mu + 4)), fma(syn_sa, nn[5], __ldg(mu + 5))};
+      } else {
+        gyro = {ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
+        acc = {ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
+      }
       const double dt = op.dt;
       const Q4 q{s.qw, s.qx, s.qy, s.qz};
       const double tx_ = 2 * q.x, ty_ = 2 * q.y, tz_ = 2 * q.z;
@@ -669,20 +688,20 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
       // ---- indexed / indexed-plus-orientation measurement ----
       const StreamDesc& st = p.streams[op.stream];
       const long long sn = st.map ? (long long)__ldg(st.map + n) : n;
-      V3 dquat{0, 0, 0};
-      if (st.has_orient) {
-        const long long SN = st.cols;
-        const double* qb = st.quat + op.row * 4 * SN + sn;
-        const Q4 mq{__ldg(qb), __ldg(qb + SN), __ldg(qb + 2 * SN), __ldg(qb + 3 * SN)};
-        dquat = subtract_quats(mq, {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
+      MeasSrc<SYN> src{};
+      if constexpr (SYN) {
+        src.ss = &p.syn.st[op.stream];
+        src.kfs = syn_kf ^ ((unsigned long long)__ldg(src.ss->step + op.row) * SYN_K2);
       }
+      V3 dquat{0, 0, 0};
+      if (st.has_orient) dquat = subtract_quats(src.quat(st, op.row, sn), {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
       const V3 chi0{s.x[6], s.x[7], s.x[8]};
       for (int ci = 0; ci < st.n_chunks; ci++) {
         const int a0 = st.chunk_start[ci];
         const int fast = st.chunk_fast[ci];
-        if (fast >= 0 && fast < 100) g_meas3<G, DC>(Pf, l, s, st, a0, fast, op.row, N, n, sn, dquat, chi0);
-        else if (fast >= 100) g_meas1<G, DC>(Pf, l, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
-        else g_meas_block<G, DC>(Pf, l, s, st, a0, st.chunk_len[ci], op.row, sn, dquat, chi0);
+        if (fast >= 0 && fast < 100) g_meas3<G, DC>(Pf, l, s, st, src, a0, fast, op.row, N, n, sn, dquat, chi0);
+        else if (fast >= 100) g_meas1<G, DC>(Pf, l, s, st, src, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
+        else g_meas_block<G, DC>(Pf, l, s, st, src, a0, st.chunk_len[ci], op.row, sn, dquat, chi0);
       }
 #ifndef RBIS_GROUP_COVONLY
       meas_finish(s, chi0, p.chi_tol, p.ctor_folds_chi, p.renorm);

@@ -244,6 +244,90 @@ struct Op {
   double dt;
 };
 
+// ---- on-device synthesis of the input rows (rbis_synth.cuh holds the kernels that MATERIALISE the rows) ----
+// key = seed ^ filter * K1 ^ step * K2 ^ channel * K3;  a = splitmix64(key), b = splitmix64(a)
+//   mode 0 (exact):  u1 = ((a >> 11) + 1) / (2^53 + 1), u2 = (b >> 11) / 2^53, n = sqrt(-2 ln u1) cos(2 pi u2) in double
+//                    -- the integer part is bit-exact against numpy (pronto_b200/synth.py:normal), the libm calls to an ulp or two;
+//   mode 1 (fast):   the same counters and hash, ONE hash per pair of channels (see syn_pair_k), ln / sqrt / cos in single
+//                    precision with the SFU approximations (n carries ~1e-6 relative error, irrelevant for a noise sample).
+// The SYN instantiations of the fused kernels draw mode-1 rows INSIDE the kernel with these same functions (same bits as the
+// materialised rows), so a Monte-Carlo ensemble reads no per-filter input from HBM at all.
+constexpr unsigned long long SYN_K1 = 0x9E3779B97F4A7C15ull, SYN_K2 = 0xC2B2AE3D27D4EB4Full, SYN_K3 = 0x165667B19E3779F9ull;
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// kfs = seed ^ filter * K1 ^ step * K2 (the caller hoists what it can)
+// Mode 1 draws channels in PAIRS (2k, 2k+1) from ONE hash of the even channel's key: radius from its top 24 bits, angle from
+// the next 24, the even channel takes r cos(theta) and the odd one r cos(theta - pi/2) -- Box-Muller's two independent
+// normals.  syn_pick(syn_pair_k(kfs, c & ~1), c & 1) is THE definition of channel c; code that needs both channels of a pair
+// evaluates the pair once and gets the same bits.
+struct SynPair {
+  float r, th;
+};
+__device__ __forceinline__ SynPair syn_pair_k(unsigned long long kfs, unsigned even_channel) {
+  const unsigned long long a = splitmix64(kfs ^ ((unsigned long long)even_channel * SYN_K3));
+  const float u1 = ((float)(unsigned)(a >> 40) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (float)((unsigned)(a >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
+  // -2 ln u1 = (-2 ln 2) lg2 u1 > 0; the SFU forms directly (sqrtf / __logf would add their range and rounding fix-ups)
+  float l2, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));
+  return {r, 6.2831853071795865f * u2};
+}
+__device__ __forceinline__ double syn_pick(const SynPair& p, unsigned odd) {
+  return (double)(p.r * __cosf(odd ? p.th - 1.5707963267948966f : p.th));
+}
+template <int MODE>
+__device__ __forceinline__ double syn_normal_k(unsigned long long kfs, unsigned channel) {
+  if constexpr (MODE == 0) {
+    const unsigned long long a = splitmix64(kfs ^ ((unsigned long long)channel * SYN_K3)), b = splitmix64(a);
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+    const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2);
+  } else {
+    return syn_pick(syn_pair_k(kfs, channel & ~1u), channel & 1u);
+  }
+}
+// channels c0 .. c0+COUNT-1 (c0 run time): one hash per pair touched
+template <int MODE, int COUNT>
+__device__ __forceinline__ void syn_normals_k(unsigned long long kfs, unsigned c0, double (&out)[COUNT]) {
+  if constexpr (MODE == 0) {
+#pragma unroll
+    for (int a = 0; a < COUNT; a++) out[a] = syn_normal_k<0>(kfs, c0 + a);
+  } else {
+    SynPair p = syn_pair_k(kfs, c0 & ~1u);
+#pragma unroll
+    for (int a = 0; a < COUNT; a++) {
+      const unsigned c = c0 + a;
+      if (a > 0 && !(c & 1u)) p = syn_pair_k(kfs, c);
+      out[a] = syn_pick(p, c & 1u);
+    }
+  }
+}
+template <int MODE>
+__device__ __forceinline__ double syn_normal(unsigned long long seed, unsigned long long filter, unsigned long long step, unsigned channel) {
+  return syn_normal_k<MODE>(seed ^ (filter * SYN_K1) ^ (step * SYN_K2), channel);
+}
+struct SynStreamK {
+  const double* mean;       // device [rows][m]
+  const double* mean_quat;  // device [rows][4] or nullptr
+  const long long* step;    // device [rows]
+  double sigma[9];
+  double sigma_rot[3];
+  int channel, channel_rot;
+};
+struct SynK {
+  unsigned long long seed;
+  long long first_filter;
+  const double* imu_mean;   // device [rows][6]
+  const long long* imu_step;
+  double sigma_gyro, sigma_accel, dt;  // sigma < 0: per filter sqrt(q / dt)
+  SynStreamK st[8];
+};
+
 struct KParams {
   long long N;
   double* vec;     // [21][N]
@@ -264,6 +348,7 @@ struct KParams {
   int ctor_folds_chi, renorm, n_snap;
   int block_offset;  // first CTA of this launch's range (launch groups)
   StreamDesc streams[MAX_STREAMS];
+  SynK syn;          // SYN kernel instantiations only
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -381,6 +466,23 @@ __device__ __forceinline__ V3 subtract_quats(const Q4& q1, const Q4& q2) {
   return {r.x / n * angle, r.y / n * angle, r.z / n * angle};
 }
 
+// ---- synthesised input rows (SYN kernels and the materialising kernels of rbis_synth.cuh share these) ----
+// measured orientation of a pose row: mean_quat (x) Exp(sigma_rot * n); plain products and sums in the order of
+// pronto_b200/synth.py (no contraction: the library is built with -fmad=false)
+template <int MODE>
+__device__ __forceinline__ Q4 syn_quat(const double* __restrict__ mq, const double (&sigma_rot)[3], unsigned long long kfs, unsigned channel_rot) {
+  double nn[3];
+  syn_normals_k<MODE, 3>(kfs, channel_rot, nn);
+  const V3 chi{sigma_rot[0] * nn[0], sigma_rot[1] * nn[1], sigma_rot[2] * nn[2]};
+  const double nrm = sqrt(chi.x * chi.x + chi.y * chi.y + chi.z * chi.z);
+  double sn = 0.0, cs = 1.0;
+  if (nrm > 0) { sincos(0.5 * nrm, &sn, &cs); sn /= nrm; }
+  const Q4 dq{cs, sn * chi.x, sn * chi.y, sn * chi.z};
+  const Q4 t{mq[0], mq[1], mq[2], mq[3]};
+  return {t.w * dq.w - t.x * dq.x - t.y * dq.y - t.z * dq.z, t.w * dq.x + t.x * dq.w + t.y * dq.z - t.z * dq.y,
+          t.w * dq.y + t.y * dq.w + t.z * dq.x - t.x * dq.z, t.w * dq.z + t.z * dq.w + t.x * dq.y - t.y * dq.x};
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tensor-memory access.  No "memory" clobbers: the asm statements are volatile, so they keep their
 // program order among themselves, while ordinary shared/global accesses may move around them.
@@ -433,6 +535,40 @@ __device__ __forceinline__ double ldg_early(const double* ptr) {
   return __ldg(ptr);
 #endif
 }
+
+// Where the rows of a measurement op come from: HBM (st.z, st.quat), or -- SYN kernels -- drawn on the spot from the
+// noise-free row and the filter's counters, with the expressions of the materialising kernels in rbis_synth.cuh.
+template <bool SYN>
+struct MeasSrc {
+  const SynStreamK* ss;    // SYN only
+  unsigned long long kfs;  // SYN only: seed ^ filter * K1 ^ step * K2
+  template <bool EARLY = true>
+  __device__ __forceinline__ double z(const StreamDesc& st, long long row, int a, long long sn) const {
+    if constexpr (SYN) return fma(ss->sigma[a], syn_normal_k<1>(kfs, (unsigned)(ss->channel + a)), __ldg(ss->mean + row * st.m + a));
+    else if constexpr (EARLY) return ldg_early(st.z + (row * st.m + a) * st.cols + sn);
+    else return __ldg(st.z + (row * st.m + a) * st.cols + sn);
+  }
+  // rows a0, a0+1, a0+2
+  __device__ __forceinline__ void z3(const StreamDesc& st, long long row, int a0, long long sn, double (&out)[3]) const {
+    if constexpr (SYN) {
+      double nn[3];
+      syn_normals_k<1, 3>(kfs, (unsigned)(ss->channel + a0), nn);
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[a] = fma(ss->sigma[a0 + a], nn[a], __ldg(ss->mean + row * st.m + a0 + a));
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * st.cols + sn);
+    }
+  }
+  __device__ __forceinline__ Q4 quat(const StreamDesc& st, long long row, long long sn) const {
+    if constexpr (SYN) return syn_quat<1>(ss->mean_quat + row * 4, ss->sigma_rot, kfs, (unsigned)ss->channel_rot);
+    else {
+      const long long SN = st.cols;
+      const double* qb = st.quat + row * 4 * SN + sn;
+      return {__ldg(qb), __ldg(qb + SN), __ldg(qb + 2 * SN), __ldg(qb + 3 * SN)};
+    }
+  }
+};
 
 // Per-lane view of the covariance.
 struct Cov {
@@ -925,8 +1061,8 @@ template <bool DC>
 __host__ __device__ constexpr int carried_pos(int c) { return DC ? act_pos(c) : c; }
 
 // DC: only the 15 active rows/columns exist (the couplings to omega / a are exactly zero, so are their gains).
-template <int I0, bool DC>
-__device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& st, int a0, long long row, long long N,
+template <int I0, bool DC, bool SYN>
+__device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, long long row, long long N,
                                       long long n, long long sn, const V3& dquat, const V3& chi0) {
   static_assert(!DC || (is_act(I0) && I0 % 3 == 0), "a DC kernel cannot update on omega / a indices");
   constexpr int NC = DC ? N_ACT : NS;        // columns of HP that are carried
@@ -936,8 +1072,7 @@ __device__ __forceinline__ void meas3(Cov& P, FilterState& s, const StreamDesc& 
   constexpr auto pos = &carried_pos<DC>;
   // issue the measurement loads first; they are consumed after the covariance work
   double z[3], Rdg[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) z[a] = ldg_early(st.z + (row * st.m + (a0 + a)) * st.cols + sn);
+  src.z3(st, row, a0, sn, z);
   if (st.r_mode == 1) {
 #pragma unroll
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
@@ -1144,12 +1279,12 @@ __device__ __forceinline__ void rank1_sweep(Cov& P, const double (&g)[DC ? N_ACT
 // that is not an aligned triple when its noise is uncorrelated with the other rows).  The index is a run-time, warp-uniform
 // value: the row P[idx, :] is fetched with run-time addressing (15 or 21 loads), everything after that -- the rank-1
 // sweep P -= h h^T / s and the state update -- runs over compile-time slots with h in registers.
-template <bool DC>
-__device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& st, int a0, int idx, long long row, long long N,
+template <bool DC, bool SYN>
+__device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int idx, long long row, long long N,
                                       long long n, long long sn, const V3& dquat, const V3& chi0) {
   constexpr int NC = DC ? N_ACT : NS;
   constexpr auto pos = &carried_pos<DC>;
-  const double z = ldg_early(st.z + (row * st.m + a0) * st.cols + sn);
+  const double z = src.z(st, row, a0, sn);
   const double Rv = (st.r_mode == 1) ? ldg_early(st.R + (long long)a0 * N + n) : __ldg(st.R + a0 + (long long)st.m * a0);
   double h[NC];
 #if RBIS_MEAS1_GETR
@@ -1190,8 +1325,8 @@ __device__ __forceinline__ void meas1(Cov& P, FilterState& s, const StreamDesc& 
 // Row a of H' combines the covariance rows idx_b, b <= a, so everything lives in registers: g = P H'_a^T (15 / 21
 // doubles), a rank-1 sweep over compile-time slots, the state update.  No local-memory arrays, no separate kernel variant.
 // Only the BLOCKS = true kernel variants contain it.
-template <bool DC>
-__device__ __forceinline__ void meas_block(Cov& P, FilterState& s, const StreamDesc& st, int a0, int M, long long row, long long N,
+template <bool DC, bool SYN>
+__device__ __forceinline__ void meas_block(Cov& P, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int M, long long row, long long N,
                                            long long n, long long sn, const V3& dquat, const V3& chi0) {
   constexpr int NC = DC ? N_ACT : NS;
   const double* W = st.R + RS_W;
@@ -1219,7 +1354,7 @@ __device__ __forceinline__ void meas_block(Cov& P, FilterState& s, const StreamD
         const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
         rb = dq - (xi - c0);
       } else {
-        rb = __ldg(st.z + (row * st.m + (a0 + b)) * st.cols + sn) - xi;
+        rb = src.template z<false>(st, row, a0 + b, sn) - xi;
       }
       rp = fma(w, rb, rp);
     }
@@ -1316,7 +1451,8 @@ __device__ __forceinline__ void store_overwritten_blocks(double* __restrict__ ds
 // ------------------------------------------------------------------------------------------------
 // DC = true is launched when the host has verified that every filter's omega / a couplings are exactly zero and no
 // measurement of the program indexes omega or a (see "decoupled filters" above).
-template <bool BLOCKS, bool DC = false>
+// SYN = true: the input rows are drawn inside the kernel (KParams::syn, mode-1 generator) instead of being read from HBM.
+template <bool BLOCKS, bool DC = false, bool SYN = false>
 #ifdef RBIS_MAXNREG  // dev probe: cap the registers directly instead of through the launch bounds
 __global__ void __maxnreg__(RBIS_MAXNREG) rbis_fused_kernel(const __grid_constant__ KParams p) {
 #else
@@ -1366,6 +1502,14 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
     return o;
   };
   const long long imu_n = p.imu_map ? (long long)__ldg(p.imu_map + n) : n;
+  // SYN: the filter's part of the counter key and its IMU noise levels
+  unsigned long long syn_kf = 0;
+  double syn_sg = 0.0, syn_sa = 0.0;
+  if constexpr (SYN) {
+    syn_kf = p.syn.seed ^ ((unsigned long long)(p.syn.first_filter + n) * SYN_K1);
+    syn_sg = p.syn.sigma_gyro >= 0 ? p.syn.sigma_gyro : sqrt(__ldg(p.q_gyro + n) / p.syn.dt);
+    syn_sa = p.syn.sigma_accel >= 0 ? p.syn.sigma_accel : sqrt(__ldg(p.q_accel + n) / p.syn.dt);
+  }
 #if RBIS_STAGGER_NS
   // the warps of a scheduler run the same program from the same start, so their FP64-dense and latency-bound phases
   // coincide; a one-time skew between the warp quartets spreads them over the step
@@ -1389,8 +1533,17 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
         qn.q_gyro_bias = ldg_early(p.q_gyro_bias + n); qn.q_accel_bias = ldg_early(p.q_accel_bias + n);
       };
       auto load_inputs = [&]() {
-        gyro = {ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
-        acc = {ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
+        if constexpr (SYN) {
+          const unsigned long long kfs = syn_kf ^ ((unsigned long long)__ldg(p.syn.imu_step + op.row) * SYN_K2);
+          const double* mu = p.syn.imu_mean + op.row * 6;
+          double nn[6];
+          syn_normals_k<1, 6>(kfs, 0u, nn);
+          gyro = {fma(syn_sg, nn[0], __ldg(mu)), fma(syn_sg, nn[1], __ldg(mu + 1)), fma(syn_sg, nn[2], __ldg(mu + 2))};
+          acc = {fma(syn_sa, nn[3], __ldg(mu + 3)), fma(syn_sa, nn[4], __ldg(mu + 4)), fma(syn_sa, nn[5], __ldg(mu + 5))};
+        } else {
+          gyro = {ldg_early(base), ldg_early(base + Ni), ldg_early(base + 2 * Ni)};
+          acc = {ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
+        }
       };
 #if !RBIS_LATE_LOADS
       load_inputs();
@@ -1479,31 +1632,31 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
       // ---- indexed / indexed-plus-orientation measurement ----
       const StreamDesc& st = p.streams[op.stream];
       const long long sn = st.map ? (long long)__ldg(st.map + n) : n;
-      V3 dquat{0, 0, 0};
-      if (st.has_orient) {
-        const long long SN = st.cols;
-        const double* qb = st.quat + op.row * 4 * SN + sn;
-        const Q4 mq{__ldg(qb), __ldg(qb + SN), __ldg(qb + 2 * SN), __ldg(qb + 3 * SN)};
-        dquat = subtract_quats(mq, {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
+      MeasSrc<SYN> src{};
+      if constexpr (SYN) {
+        src.ss = &p.syn.st[op.stream];
+        src.kfs = syn_kf ^ ((unsigned long long)__ldg(src.ss->step + op.row) * SYN_K2);
       }
+      V3 dquat{0, 0, 0};
+      if (st.has_orient) dquat = subtract_quats(src.quat(st, op.row, sn), {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
       const V3 chi0{s.x[6], s.x[7], s.x[8]};
       for (int ci = 0; ci < st.n_chunks; ci++) {
         const int a0 = st.chunk_start[ci];
         const int fast = st.chunk_fast[ci];
         switch (fast) {
-          case 0: if constexpr (!DC) meas3<0, false>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 3: meas3<3, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 6: meas3<6, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 9: meas3<9, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 12: if constexpr (!DC) meas3<12, false>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 15: meas3<15, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
-          case 18: meas3<18, DC>(P, s, st, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 0: if constexpr (!DC) meas3<0, false>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 3: meas3<3, DC>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 6: meas3<6, DC>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 9: meas3<9, DC>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 12: if constexpr (!DC) meas3<12, false>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 15: meas3<15, DC>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
+          case 18: meas3<18, DC>(P, s, st, src, a0, op.row, N, n, sn, dquat, chi0); break;
           default:
             if constexpr (BLOCKS) {
               if (fast >= 100) {  // one-row chunk on state index fast - 100
-                meas1<DC>(P, s, st, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
+                meas1<DC>(P, s, st, src, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
               } else {            // correlated rows: decorrelated scalar updates
-                meas_block<DC>(P, s, st, a0, st.chunk_len[ci], op.row, N, n, sn, dquat, chi0);
+                meas_block<DC>(P, s, st, src, a0, st.chunk_len[ci], op.row, N, n, sn, dquat, chi0);
               }
             }
             break;

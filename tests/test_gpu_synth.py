@@ -46,16 +46,25 @@ def test_exact_mode_reproduces_the_numpy_generator():
     assert np.max(np.abs(again["imu"].cpu().numpy() - got["imu"].cpu().numpy())) < 1e-15
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_fused_run_over_synthesised_inputs_equals_run_over_materialised_rows(oracle, mode):
+@pytest.mark.parametrize("mode,mapping,materialize", [(0, 0, False), (1, 1, False), (1, 4, False), (1, 8, False), (1, 1, True), (1, 0, False)])
+def test_fused_run_over_synthesised_inputs_equals_run_over_materialised_rows(oracle, mode, mapping, materialize):
+    """mode 1 on a decoupled ensemble draws the rows INSIDE the fused kernel (SYN instantiations of the lane-per-filter and
+    warp-group kernels) unless synth_materialize is set; mode 0 always materialises them first.  Same bits every way."""
     N, T = 300, 220
     sc = scenario(N, T, tumbling=True)
     st = sc["st"]
-    with RBISBatch(N) as b:
+    with RBISBatch(N, mapping=mapping, synth_materialize=materialize) as b:
         b.set_process_noise(*nominal_q())
         b.set_state(sc["vec"], sc["quat"], sc["cov"])
         spec = _spec(sc["truth"], 0, T, mode=mode)
+        l0 = b.launch_count
         b.run_fused_synth(st["events"], _streams(st), spec)
+        # fused synthesis = the coupling check + the fused kernel(s) and nothing else; materialising adds three generator kernels
+        n_launched = b.launch_count - l0
+        assert (n_launched <= 2) == (mode == 1 and not materialize), n_launched
+        assert bool(b.last_kernel_variant & 4) == (mode == 1 and not materialize)   # the SYN kernel instantiation ran
+        if mapping > 1:
+            assert b.last_kernel_variant >> 4 == mapping
         a = b.get_state()
         rows = b.synthesize(spec)
         b.set_state(sc["vec"], sc["quat"], sc["cov"])
