@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""dev/ws_bench.py -- small-ensemble timings of the three mappings through the C ABI: device-resident inputs, back-to-back launches."""
+"""dev/mapping_bench.py -- small-ensemble timings of the three mappings through the C ABI: device-resident inputs, back-to-back launches."""
 import os, sys, time
 import numpy as np
 import torch
@@ -20,7 +20,7 @@ for N, kind in cases:
     vec0, quat0, cov0 = bench.initial_state(N, gen, dev)
     chunks = [bench.device_chunk(truth, c * Tc, Tc, N, gen, dev) for c in range(K)]
     ref = None
-    for mapping in [int(m) for m in os.environ.get("WS_MAPPINGS", "1,4,8,32").split(",")]:
+    for mapping in [int(m) for m in os.environ.get("MAPPINGS", "1,4,8").split(",")]:
         with RBISBatch(N, mapping=mapping) as b:
             b.set_process_noise(p["q_gyro"], p["q_accel"], p["q_gyro_bias"], p["q_accel_bias"])
             b.set_state(vec0, quat0, cov0)

@@ -107,7 +107,7 @@ struct rbis_batch {
   int64_t notch_cols = 0;
   DevBuf notch_stage;               // device copy of a host chunk
   int last_variant = -1;  // kernel variant of the last fused launch: bit 1 decoupled, bit 0 with meas_block, bit 2 SYN (rows drawn in the kernel), bits 4.. lanes per filter (0 = one)
-  int mapping = 1;        // lanes per filter of the fused kernels: 1 = lane-per-filter kernels, 2/4/8/16 = warp-group kernels, 32 = warp-specialised kernels
+  int mapping = 1;        // lanes per filter of the fused kernels: 1 = lane-per-filter kernels, 2/4/8/16 = warp-group kernels
   int lane_tpb = 384;     // filters per CTA of the decoupled lane-per-filter kernels (384, 256, 128)
   int n_sms = 148;
   long long last_part = -1;  // filters per launch-group range of the last grouped launch (ranges differ between kernel variants)
@@ -195,14 +195,6 @@ LaunchGeom launch_geom(int variant, int mapping, int lane_tpb, long long N, int 
     g.threads = g.tu ? g.tu->threads : rbisk::TPB;
     g.smem = g.tu ? g.tu->smem : rbisk::SMEM_BYTES;
     g.fpc = g.threads;
-  } else if (mapping == 32) {
-    // warp-specialised kernels: teams of 32 filters, one team per CTA while that fills the SMs, else two
-    g.tu = &rbis_fused_tu_ws;
-    const long long teams = (N + g.tu->filters_per_warp - 1) / g.tu->filters_per_warp;
-    const int tpc = teams > n_sms ? g.tu->max_warps : 1;
-    g.threads = g.tu->threads * tpc;
-    g.smem = g.tu->smem * tpc;
-    g.fpc = (long long)g.tu->filters_per_warp * tpc;
   } else {
     // warps per CTA so that the ensemble spreads over all SMs in whole waves
     g.tu = group_tu(mapping);
@@ -561,7 +553,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   // Synthesised inputs: the decoupled kernels have SYN instantiations that draw the rows themselves (mode 1), so nothing is
   // materialised and the launch reads no per-filter input; otherwise the rows are generated into the staging slot first.
   const bool fuse_syn = syn != nullptr && syn->mode == 1 && !h->cfg.synth_materialize && (variant & 2) != 0 &&
-                        ((h->mapping > 1 && h->mapping != 32) || !(variant & 1));
+                        (h->mapping > 1 || !(variant & 1));
   if (syn) {
     if (kp.imu_map) return fail(RBIS_ERR_STATE, "synthesised inputs draw one column per filter: clear the column maps first");
     for (int s = 0; s < n_streams; s++)
@@ -667,10 +659,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     }
   }
   if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
-  // The warp-specialised kernels take decoupled programs whose chunks are all aligned triples; anything else of a handle
-  // mapped to them runs on the 4-lane warp-group kernels (same bits, so switching per launch is invisible).
-  const int mapping = (h->mapping == 32 && !((variant & 2) && !(variant & 1))) ? 4 : h->mapping;
-  const LaunchGeom geom = launch_geom(variant, mapping, h->lane_tpb, N, h->n_sms);
+  const LaunchGeom geom = launch_geom(variant, h->mapping, h->lane_tpb, N, h->n_sms);
   const unsigned grid = geom.grid;
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
@@ -789,7 +778,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
       if (f == 2) f = as_launch;
   }
   h->snap_dc = snap_dc;
-  h->last_variant = variant | (fuse_syn ? 4 : 0) | (mapping > 1 ? (mapping << 4) : 0);
+  h->last_variant = variant | (fuse_syn ? 4 : 0) | (h->mapping > 1 ? (h->mapping << 4) : 0);
   h->utime = last_utime;
   return 0;
 }
@@ -825,8 +814,8 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   if (c.snapshot_slots < 0) return fail(RBIS_ERR_INVALID, "snapshot_slots must be >= 0");
   if (c.launch_groups < 0 || c.launch_groups > rbis_batch::kMaxGroups)
     return fail(RBIS_ERR_INVALID, "launch_groups must be in [0, %d]", rbis_batch::kMaxGroups);
-  if (c.mapping != 0 && c.mapping != 1 && c.mapping != 2 && c.mapping != 4 && c.mapping != 8 && c.mapping != 16 && c.mapping != 32)
-    return fail(RBIS_ERR_INVALID, "mapping must be 0 (automatic), 1, 2, 4, 8, 16 (lanes per filter) or 32 (warp-specialised)");
+  if (c.mapping != 0 && c.mapping != 1 && c.mapping != 2 && c.mapping != 4 && c.mapping != 8 && c.mapping != 16)
+    return fail(RBIS_ERR_INVALID, "mapping must be 0 (automatic), 1, 2, 4, 8 or 16 lanes per filter");
   if (c.piece_ops < 0 || (c.piece_ops > 0 && c.piece_ops < 8)) return fail(RBIS_ERR_INVALID, "piece_ops must be 0 (automatic) or >= 8");
   if (c.lane_filters_per_cta != 0 && c.lane_filters_per_cta != 384 && c.lane_filters_per_cta != 256 && c.lane_filters_per_cta != 128)
     return fail(RBIS_ERR_INVALID, "lane_filters_per_cta must be 0 (automatic), 384, 256 or 128");
@@ -859,7 +848,6 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
       if (t->kparams_bytes != sizeof(rbisk::KParams)) { fail(RBIS_ERR_CUDA, "kernel parameter block mismatch between translation units"); rbis_batch_destroy(h); return RBIS_ERR_CUDA; }
     for (const rbis_fused_tu_t* t : kGroupTus)
       if (t->kparams_bytes != sizeof(rbisk::KParams)) { fail(RBIS_ERR_CUDA, "kernel parameter block mismatch between translation units"); rbis_batch_destroy(h); return RBIS_ERR_CUDA; }
-    if (rbis_fused_tu_ws.kparams_bytes != sizeof(rbisk::KParams)) { fail(RBIS_ERR_CUDA, "kernel parameter block mismatch between translation units"); rbis_batch_destroy(h); return RBIS_ERR_CUDA; }
   }
   const size_t N = (size_t)n_filters;
   auto cleanup = [&](int code) { rbis_batch_destroy(h); return code; };
@@ -918,7 +906,6 @@ int rbis_batch_create(rbis_batch_t** out, int64_t n_filters, const rbis_batch_co
   CREATE_TRY(cudaFuncSetAttribute(rbisk::rbis_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   for (const rbis_fused_tu_t* t : kLaneTus) CREATE_TRY(t->prepare());
   for (const rbis_fused_tu_t* t : kGroupTus) CREATE_TRY(t->prepare());
-  CREATE_TRY(rbis_fused_tu_ws.prepare());
   // default state: zeros, identity quaternion, zero covariance, zero process noise
   CREATE_TRY(cudaMemsetAsync(h->vec, 0, N * 21 * sizeof(double), h->stream));
   CREATE_TRY(cudaMemsetAsync(h->quat, 0, N * 4 * sizeof(double), h->stream));

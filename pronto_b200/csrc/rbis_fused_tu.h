@@ -19,6 +19,5 @@ struct rbis_fused_tu_t {
 extern "C" {
 extern const rbis_fused_tu_t rbis_fused_tu_dc384, rbis_fused_tu_dc256, rbis_fused_tu_dc128;
 extern const rbis_fused_tu_t rbis_fused_tu_g2, rbis_fused_tu_g4, rbis_fused_tu_g8, rbis_fused_tu_g16;
-extern const rbis_fused_tu_t rbis_fused_tu_ws;  // warp-specialised kernels: threads / smem are those of ONE team, max_warps = teams per CTA
 }
 #endif

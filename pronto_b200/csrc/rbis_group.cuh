@@ -3,25 +3,21 @@
 // Why it exists.  The lane-per-filter kernels of rbis_kernels.cuh need >= 148 x 384 filters to fill a
 // B200; a 4,096-filter ensemble (BASELINE configs[1]) or a 65,536-filter ensemble split over 8 GPUs (8,192 each) leaves
 // 11-22 of 148 SMs busy and every busy scheduler latency bound.  Here a filter's work is spread over G lanes, so the same
-// ensemble brings G times as many warps and each warp's dependent chain per step is several times shorter.
+// ensemble brings G times as many warps and each warp's dependent chain per step is ~G times shorter.
 //
-// Layout.  Everything a filter owns lives in SHARED MEMORY for the whole program -- registers hold only what the running
-// phase needs, so that 14-16 warps fit on an SM:
-//   * the covariance as a FULL NA x NA matrix, row-major, NA = 15 (DC: the active block v, chi, p, b_g, b_a; see
-//     "decoupled filters" in rbis_kernels.cuh) or 21 (dense), with BOTH triangles kept equal bit for bit: every element
-//     (i, j) is computed once, by the lane that owns column max(i, j), and stored to (i, j) and (j, i);
-//   * the filter state (21 + 4 + log-likelihood) and the four process-noise values: 30 doubles, read as broadcasts;
-//   * a 3 x NA scratch for Y = L^-1 P[idx,:] of a measurement update.
-// The leading dimension NA is odd and the per-filter stride is = G (mod 16) doubles, which makes the column accesses
-// (lane l -> column l + G j), their mirrored row accesses and the broadcast reads conflict free for 8-byte accesses.
-// The serial state arithmetic (insUpdateState, the 3x3 LDL^T, addState) is evaluated by every lane of the group from the
-// shared copy, with the device functions of the lane-per-filter kernel, and written back by lane 0; the lanes split the
-// covariance work by columns and the state update of a measurement by components:
+// Layout.  A filter's covariance lives in shared memory as a FULL NA x NA matrix, row-major, NA = 15 (DC: the active
+// block v, chi, p, b_g, b_a; see "decoupled filters" in rbis_kernels.cuh) or 21 (dense), with BOTH triangles kept equal
+// bit for bit: every element (i, j) is computed once, by the lane that owns column max(i, j), and stored to (i, j) and
+// (j, i).  The packed upper triangle is read at the start of a launch / RESTORE and written at its end / SNAPSHOT.  The
+// leading dimension NA is odd and the per-filter stride is = G (mod 16) doubles, which makes the column accesses (lane l ->
+// column l + G j), their mirrored row accesses and the broadcast reads of whole rows conflict free for 8-byte accesses.
+// The filter state (21 + 4 + log-likelihood) is REPLICATED in the G lanes of the group: every lane runs the serial state
+// arithmetic (insUpdateState, the 3x3 LDL^T, addState) redundantly, with the device functions of the lane-per-filter
+// kernel, and the lanes split the covariance work by columns:
 //   IMU step  cov = Ad cov Ad^T + Qd (MSE/rbis.cpp:113-118) as the three congruences Ad = E_chi E_v E_p of
 //             rbisk::cov_propagate, each a column pass (lane owns columns) and a 3-row pass, see g_cov_propagate;
-//   update    S = R + P[idx,idx] and its LDL^T in every lane, Y = L^-1 P[idx,:] by the owners of the columns (published in
-//             the scratch), then P[i,j] -= sum_a Y[a][i] Y[a][j] / d_a for i <= j in the lane's own columns j and
-//             x_c += sum_a Y[a][c] u_a for its own components c (rbis.cpp:134-140).
+//   update    S = R + P[idx,idx], LDL^T and Y = L^-1 P[idx,:] in every lane (broadcast reads of the three rows), then
+//             P[i,j] -= sum_a Y[a][i] Y[a][j] / d_a for i <= j in the lane's own columns j (rbis.cpp:134-140).
 // EVERY ELEMENT IS COMPUTED BY THE SAME EXPRESSION AS IN THE LANE-PER-FILTER KERNELS (the library is compiled with
 // -fmad=false and every fused multiply-add is explicit), so the two mappings give bit-identical results: the mapping is
 // a scheduling decision the caller cannot observe (tests/test_gpu_group.py), and statistics of a sharded ensemble do
@@ -29,14 +25,15 @@
 // Lanes synchronise with __syncwarp() only; a CTA is any number of warps (chosen by the host so that the ensemble
 // spreads over all SMs), there is no CTA-wide barrier and no tensor memory.
 //
-// Included by the rbis_fused_g*.cu translation units after rbis_kernels.cuh.
+// Included by rbis_batch.cu after the first (default-configuration) inclusion of rbis_kernels.cuh.
 #ifndef RBIS_GROUP_CUH_
 #define RBIS_GROUP_CUH_
+#ifndef RBIS_GROUP_STATE_FIRST
+#define RBIS_GROUP_STATE_FIRST 0  // insUpdateState before (1) or after (0) the covariance passes of an IMU step (dev knob; 0 measured 5-10 % faster)
+#endif
 
 namespace rbisk {
 namespace grp {
-
-constexpr int XS_Q = 21, XS_LL = 25, XS_QN = 26, XS_LEN = 30;  // state block: vec[21], quat[4], loglik, q_gyro, q_accel, q_gyro_bias, q_accel_bias
 
 template <int G, bool DC>
 struct Geo {
@@ -45,10 +42,8 @@ struct Geo {
   static constexpr int LD = NA;                // leading dimension (odd: 15 or 21)
   static constexpr int FPW = 32 / G;           // filters per warp
   static constexpr int NJ = (NA + G - 1) / G;  // columns (rows) a lane owns at most
-  static constexpr int XS = NA * LD;           // offset of the state block
-  static constexpr int YS = (XS + XS_LEN + 1) & ~1;  // offset of the Y scratch [NA][4] (16-byte aligned)
   static constexpr int stride_() {
-    int s = YS + 4 * NA;
+    int s = NA * LD;
     while (s % 16 != G % 16) s++;
     return s;
   }
@@ -60,11 +55,32 @@ template <bool DC>
 __device__ __forceinline__ int pos_of(int idx) { return DC ? (idx < 12 ? idx - 3 : idx - 6) : idx; }
 template <bool DC>
 __host__ __device__ constexpr int idx_of(int pos) { return DC ? act_col(pos) : pos; }
-template <bool DC>
-__device__ __forceinline__ int idx_of_rt(int pos) { return DC ? (pos < 9 ? pos + 3 : pos + 6) : pos; }
 
+// x[I0 + A] for an aligned triple base I0 in {0, 3, .., 18} (run time, warp uniform)
+template <int A>
+__device__ __forceinline__ double pick_triple(const double (&x)[NS], int I0) {
+  double v = x[A];
+#pragma unroll
+  for (int t = 1; t < NS / 3; t++) v = (I0 == 3 * t) ? x[3 * t + A] : v;
+  return v;
+}
 __device__ __forceinline__ double sel3(const V3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
-__device__ __forceinline__ V3 ld3(const double* b, int stride) { return {b[0], b[stride], b[2 * stride]}; }
+// The lane's j-th column: index, and whether it exists (lanes beyond the matrix edge work on a copy of the last column
+// and do not store, which keeps the code free of branches).
+template <int G, int NA>
+struct Own {
+  static constexpr int NJ = (NA + G - 1) / G;
+  int c[NJ];
+  bool own[NJ];
+  __device__ __forceinline__ explicit Own(int l) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int cj = l + G * j;
+      own[j] = ((j + 1) * G <= NA) || cj < NA;
+      c[j] = own[j] ? cj : NA - 1;
+    }
+  }
+};
 // One row of acc_mul_skew<SIGN>(acc, Z, u) (rbis_kernels.cuh): acc[k], Z[k] are component i of the k-th column vector.
 template <int SIGN>
 __device__ __forceinline__ void row_mul_skew(double (&acc)[3], const double (&Z)[3], const V3& u) {
@@ -73,48 +89,11 @@ __device__ __forceinline__ void row_mul_skew(double (&acc)[3], const double (&Z)
   acc[1] = fma(ux, Z[2], fma(-uz, Z[0], acc[1]));
   acc[2] = fma(uy, Z[0], fma(-ux, Z[1], acc[2]));
 }
-
-// What a lane knows about its place in the group, computed once per kernel: pointers to its columns / mirrored rows (all
-// later addresses are these plus compile-time offsets).  Lanes beyond the matrix edge work on a copy of the last column
-// and never store (own<J>() false for their last slot), which keeps the arithmetic free of branches.
-template <int G, bool DC>
-struct Ctx {
-  using GE = Geo<G, DC>;
-  static constexpr int NJ = GE::NJ, NA = GE::NA, LD = GE::LD;
-  static constexpr int NR = (3 + G - 1) / G;  // rows of a 3-row pass per lane (1 for G >= 4)
-  double* Pf;       // the filter's matrix
-  double* xs;       // state block
-  double* Ys;       // Y scratch
-  double* col[NJ];  // Pf + c_j
-  double* row[NJ];  // Pf + c_j * LD
-  int c[NJ];
-  bool own_last;    // does the lane's last column slot exist
-  int l;
-  int ri[NR];       // the lane's rows of a row pass: component i = l + G jr (< 3), clamped
-  bool rown[NR];
-  __device__ __forceinline__ Ctx(double* base, int lane_in_group) : Pf(base), xs(base + GE::XS), Ys(base + GE::YS), own_last(true), l(lane_in_group) {
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const int cj = l + G * j;
-      const bool o = ((j + 1) * G <= NA) || cj < NA;
-      if (j == NJ - 1) own_last = o;
-      c[j] = o ? cj : NA - 1;
-      col[j] = Pf + c[j];
-      row[j] = Pf + c[j] * LD;
-    }
-#pragma unroll
-    for (int jr = 0; jr < NR; jr++) { const int i = l + G * jr; rown[jr] = i < 3; ri[jr] = rown[jr] ? i : 2; }
-  }
-  template <int J>
-  __device__ __forceinline__ bool own() const {
-    if constexpr ((J + 1) * G <= NA) return true;
-    else return own_last;
-  }
-};
+__device__ __forceinline__ V3 ld3(const double* b, int stride) { return {b[0], b[stride], b[2 * stride]}; }
 
 // ------------------------------------------------------------------------------------------------
-// insUpdateCovariance (rbis.cpp:77-122) for one filter.  The same three in-place symmetric congruences
-// Ad = E_chi E_v E_p as rbisk::cov_propagate, element for element the same expressions:
+// insUpdateCovariance (rbis.cpp:77-122) for one filter; l = lane within the group.  The same three in-place symmetric
+// congruences Ad = E_chi E_v E_p as rbisk::cov_propagate, element for element the same expressions:
 //   column pass of E_X   z_c = (E_X P)[X, c] for every column c -- the lane's own columns, zp / zv / zc of rbis_kernels.cuh;
 //                        stored as P[X, c] and mirrored to P[c, X]; for c inside X the 3x3 block is left unsymmetric
 //                        (element (X_i, X_k) = z of column X_k) until
@@ -125,31 +104,37 @@ struct Ctx {
 // each phase = loads, __syncwarp, arithmetic + stores, __syncwarp (a store of one lane never overtakes another lane's load).
 // ------------------------------------------------------------------------------------------------
 template <int G, bool DC>
-__device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin& L, const QNoise& qn) {
+__device__ __forceinline__ void g_cov_propagate(double* Pf, const int l, const Lin& L, const QNoise& qn) {
   using GE = Geo<G, DC>;
-  constexpr int LD = GE::LD, NJ = GE::NJ, NR = Ctx<G, DC>::NR;
+  constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
   constexpr int PV = GE::PV, PC = GE::PC, PP = GE::PP, PG = GE::PG, PA = GE::PA;
-  double* const Pf = cx.Pf;
+  constexpr int NR = (3 + G - 1) / G;  // rows of a 3-row pass per lane (1 for G >= 4)
+  const Own<G, NA> w(l);
   const double dt = L.dt;
   const double qg = qn.q_gyro * dt, qa = qn.q_accel * dt;
+  // the lane's rows of a row pass: component i = l + G jr (< 3)
+  int ri[NR];
+  bool rown[NR];
+#pragma unroll
+  for (int jr = 0; jr < NR; jr++) { const int i = l + G * jr; rown[jr] = i < 3; ri[jr] = rown[jr] ? i : 2; }
 
   // ---------------- phase A: E_p columns.  z = zp(P[v,c], P[chi,c], P[p,c]) -> P[p,c] ----------------
   {
     V3 z[NJ];
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const double* b = cx.col[j];
+      const double* b = Pf + w.c[j];
       z[j] = zp(L, ld3(b + PV * LD, LD), ld3(b + PC * LD, LD), ld3(b + PP * LD, LD));
     });
     __syncwarp();
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const int c = cx.c[j];
-      if (cx.template own<j>()) {
-        double* b = cx.col[j];
+      const int c = w.c[j];
+      if (w.own[j]) {
+        double* b = Pf + c;
         b[PP * LD] = z[j].x; b[(PP + 1) * LD] = z[j].y; b[(PP + 2) * LD] = z[j].z;
         if (c < PP || c >= PP + 3) {  // mirror, except inside the (p,p) block (completed by the row pass)
-          double* m = cx.row[j] + PP;
+          double* m = Pf + c * LD + PP;
           m[0] = z[j].x; m[1] = z[j].y; m[2] = z[j].z;
         }
       }
@@ -161,7 +146,7 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     double outp[NR][3];
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      const double* r = Pf + (PP + cx.ri[jr]) * LD;
+      const double* r = Pf + (PP + ri[jr]) * LD;
       double T[3] = {r[PV], r[PV + 1], r[PV + 2]};
       const double Zb[3] = {r[PC], r[PC + 1], r[PC + 2]};
       const double Zp[3] = {r[PP], r[PP + 1], r[PP + 2]};
@@ -173,16 +158,16 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     double pad[NJ];  // the column's own diagonal element when it is a b_a column
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const double* b = cx.col[j];
+      const double* b = Pf + w.c[j];
       const V3 pa = ld3(b + PA * LD, LD);
       z[j] = zv(L, ld3(b + PV * LD, LD), ld3(b + PC * LD, LD), ld3(b + PG * LD, LD), pa);
-      pad[j] = sel3(pa, cx.c[j] - PA);
+      pad[j] = sel3(pa, w.c[j] - PA);
     });
     __syncwarp();
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      if (cx.rown[jr]) {
-        const int i = cx.ri[jr];
+      if (rown[jr]) {
+        const int i = ri[jr];
 #pragma unroll
         for (int j = 0; j < 3; j++)
           if (j >= i) { Pf[(PP + i) * LD + PP + j] = outp[jr][j]; Pf[(PP + j) * LD + PP + i] = outp[jr][j]; }
@@ -190,15 +175,15 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     }
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const int c = cx.c[j];
-      if (cx.template own<j>()) {
-        double* b = cx.col[j];
+      const int c = w.c[j];
+      if (w.own[j]) {
+        double* b = Pf + c;
         b[PV * LD] = z[j].x; b[(PV + 1) * LD] = z[j].y; b[(PV + 2) * LD] = z[j].z;
         if (c < PV || c >= PV + 3) {
-          double* m = cx.row[j] + PV;
+          double* m = Pf + c * LD + PV;
           m[0] = z[j].x; m[1] = z[j].y; m[2] = z[j].z;
         }
-        if (c >= PA && c < PA + 3) cx.row[j][c] = fma(qn.q_accel_bias, dt, pad[j]);  // Qd[ba,ba]
+        if (c >= PA && c < PA + 3) b[c * LD] = fma(qn.q_accel_bias, dt, pad[j]);  // Qd[ba,ba]
       }
     });
     __syncwarp();
@@ -209,7 +194,7 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     double outv[NR][3];
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      const int i = cx.ri[jr];
+      const int i = ri[jr];
       const double* r = Pf + (PV + i) * LD;
       const double Zv[3] = {r[PV], r[PV + 1], r[PV + 2]};
       const double Zc[3] = {r[PC], r[PC + 1], r[PC + 2]};
@@ -231,8 +216,8 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     double pgd[NJ];
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const int c = cx.c[j];
-      const double* b = cx.col[j];
+      const int c = w.c[j];
+      const double* b = Pf + c;
       const V3 pg = ld3(b + PG * LD, LD);
       V3 zz = zc(L, ld3(b + PC * LD, LD), pg);
       pgd[j] = sel3(pg, c - PG);
@@ -249,8 +234,8 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     __syncwarp();
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      if (cx.rown[jr]) {
-        const int i = cx.ri[jr];
+      if (rown[jr]) {
+        const int i = ri[jr];
 #pragma unroll
         for (int j = 0; j < 3; j++)
           if (j >= i) { Pf[(PV + i) * LD + PV + j] = outv[jr][j]; Pf[(PV + j) * LD + PV + i] = outv[jr][j]; }
@@ -258,15 +243,15 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     }
     static_for<NJ>([&](auto jc) {
       constexpr int j = jc;
-      const int c = cx.c[j];
-      if (cx.template own<j>()) {
-        double* b = cx.col[j];
+      const int c = w.c[j];
+      if (w.own[j]) {
+        double* b = Pf + c;
         b[PC * LD] = z[j].x; b[(PC + 1) * LD] = z[j].y; b[(PC + 2) * LD] = z[j].z;
         if (c < PC || c >= PC + 3) {
-          double* m = cx.row[j] + PC;
+          double* m = Pf + c * LD + PC;
           m[0] = z[j].x; m[1] = z[j].y; m[2] = z[j].z;
         }
-        if (c >= PG && c < PG + 3) cx.row[j][c] = fma(qn.q_gyro_bias, dt, pgd[j]);  // Qd[bg,bg]
+        if (c >= PG && c < PG + 3) b[c * LD] = fma(qn.q_gyro_bias, dt, pgd[j]);  // Qd[bg,bg]
       }
     });
     __syncwarp();
@@ -276,7 +261,7 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     double outc[NR][3];
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      const int i = cx.ri[jr];
+      const int i = ri[jr];
       const double* r = Pf + (PC + i) * LD;
       const double Zc[3] = {r[PC], r[PC + 1], r[PC + 2]};
       const double Zg[3] = {r[PG], r[PG + 1], r[PG + 2]};
@@ -290,8 +275,8 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
     __syncwarp();
 #pragma unroll
     for (int jr = 0; jr < NR; jr++) {
-      if (cx.rown[jr]) {
-        const int i = cx.ri[jr];
+      if (rown[jr]) {
+        const int i = ri[jr];
 #pragma unroll
         for (int j = 0; j < 3; j++)
           if (j >= i) { Pf[(PC + i) * LD + PC + j] = outc[jr][j]; Pf[(PC + j) * LD + PC + i] = outc[jr][j]; }
@@ -301,8 +286,8 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
       // overwrites of rbis.cpp:120-121: the owner of a column omega_k / a_k rewrites its three block elements
       static_for<NJ>([&](auto jc) {
         constexpr int j = jc;
-        const int c = cx.c[j];
-        if (cx.template own<j>()) {
+        const int c = w.c[j];
+        if (w.own[j]) {
           if (c < 3) { Pf[c] = c == 0 ? qn.q_gyro : 0.0; Pf[LD + c] = c == 1 ? qn.q_gyro : 0.0; Pf[2 * LD + c] = c == 2 ? qn.q_gyro : 0.0; }
           if (c >= 12 && c < 15) {
             Pf[12 * LD + c] = c == 12 ? qn.q_accel : 0.0; Pf[13 * LD + c] = c == 13 ? qn.q_accel : 0.0; Pf[14 * LD + c] = c == 14 ? qn.q_accel : 0.0;
@@ -315,59 +300,59 @@ __device__ __forceinline__ void g_cov_propagate(const Ctx<G, DC>& cx, const Lin&
 }
 
 // P[i,j] -= sum_a Y[a][i] (Y[a][j] r_a) over the upper triangle i <= j of the lane's own columns j, mirrored into the lower
-// triangle: the expression of rbisk::meas3 / rank1_sweep element for element.  NY = rows of Y (3 or 1); Y[a][k] is read from
-// the scratch (published by the owners of column k before the __syncwarp that precedes the sweep), wj[j][a] = the lane's own
-// Y[a][c_j] * r_a.  Column slot j only visits rows k < G (j + 1): the rest lie below the diagonal for every lane.
+// triangle: the expression of rbisk::meas3 / rank1_sweep element for element.  NY = rows of Y (3 or 1).  wj[j][a] = the
+// lane's own Y[a][c_j] * r_a, formed BEFORE the barrier that precedes the sweep (a mirrored store of another lane may
+// overwrite the lower-triangle element it was read from).  Column slot j only visits rows k < G (j + 1): the rest lie
+// below the diagonal for every lane.
 template <int G, bool DC, int NY>
-__device__ __forceinline__ void g_sweep(const Ctx<G, DC>& cx, const double (&wj)[Geo<G, DC>::NJ][NY]) {
+__device__ __forceinline__ void g_sweep(double* Pf, const Own<G, Geo<G, DC>::NA>& w, const double (&Y)[NY][Geo<G, DC>::NA],
+                                        const double (&wj)[Geo<G, DC>::NJ][NY]) {
   using GE = Geo<G, DC>;
   constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
-  static_for<NA>([&](auto kc) {
-    constexpr int k = kc;
-    double yk[NY];
-    if constexpr (NY == 3) {
-      const double2 y01 = *reinterpret_cast<const double2*>(cx.Ys + 4 * k);
-      yk[0] = y01.x; yk[1] = y01.y; yk[2] = cx.Ys[4 * k + 2];
-    } else {
-      yk[0] = cx.Ys[4 * k];
-    }
-    static_for<NJ>([&](auto jc) {
-      constexpr int j = jc;
-      constexpr int KMAX = (G * (j + 1) < NA) ? G * (j + 1) : NA;
-      if constexpr (k < KMAX) {
-        double acc = cx.col[j][k * LD];
+  static_for<NJ>([&](auto jc) {
+    constexpr int j = jc;
+    constexpr int KMAX = (G * (j + 1) < NA) ? G * (j + 1) : NA;
+    const int c = w.c[j];
+    double* b = Pf + c;
+    double* m = Pf + c * LD;
+    double v[KMAX];
 #pragma unroll
-        for (int a = NY - 1; a >= 0; a--) acc = fma(-yk[a], wj[j][a], acc);
-        if (cx.template own<j>() && (k < G * j || k <= cx.c[j])) { cx.col[j][k * LD] = acc; cx.row[j][k] = acc; }
-      }
-    });
+    for (int k = 0; k < KMAX; k++) v[k] = b[k * LD];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      double acc = v[k];
+#pragma unroll
+      for (int a = NY - 1; a >= 0; a--) acc = fma(-Y[a][k], wj[j][a], acc);
+      if (w.own[j] && (k < G * j || k <= c)) { b[k * LD] = acc; m[k] = acc; }
+    }
   });
 }
 
 // Aligned index triple I0..I0+2 (leg-odometry velocity, pose position / orientation, ...): rbis.cpp:124-143 with
 // S = L D L^T, Y = L^-1 P[idx,:], P -= Y^T D^-1 Y, x += Y^T D^-1 L^-1 r.  Same arithmetic as rbisk::meas3.
 template <int G, bool DC, bool SYN>
-__device__ __forceinline__ void g_meas3(const Ctx<G, DC>& cx, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int I0,
+__device__ __forceinline__ void g_meas3(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int I0,
                                         long long row, long long N, long long n, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
-  constexpr int LD = GE::LD, NJ = GE::NJ;
+  constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
   double z[3], Rdg[3];
   src.z3(st, row, a0, sn, z);
   if (st.r_mode == 1) {
 #pragma unroll
     for (int a = 0; a < 3; a++) Rdg[a] = ldg_early(st.R + (long long)(a0 + a) * N + n);
   }
+  const Own<G, NA> w(l);
   const int p0 = pos_of<DC>(I0);
-  // rows p0, p0+1, p0+2 of P: HP = C cov (rbis.cpp:134); the lane's own columns of them
-  double yo[NJ][3];
+  const double* r0p = Pf + p0 * LD;  // rows p0, p0+1, p0+2 of P: HP = C cov (rbis.cpp:134)
+  double Y[3][NA];
 #pragma unroll
-  for (int j = 0; j < NJ; j++) {
-    const double* b = cx.col[j] + p0 * LD;
-    yo[j][0] = b[0]; yo[j][1] = b[LD]; yo[j][2] = b[2 * LD];
-  }
+  for (int k = 0; k < NA; k++) { Y[0][k] = r0p[k]; Y[1][k] = r0p[LD + k]; Y[2][k] = r0p[2 * LD + k]; }
+  double yo[NJ][3];  // the lane's own columns of HP
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { yo[j][0] = r0p[w.c[j]]; yo[j][1] = r0p[LD + w.c[j]]; yo[j][2] = r0p[2 * LD + w.c[j]]; }
   // S = R + P[idx,idx]
-  const double* sp = cx.Pf + p0 * LD + p0;
-  double S00 = sp[0], S10 = sp[LD], S20 = sp[2 * LD], S11 = sp[LD + 1], S21 = sp[2 * LD + 1], S22 = sp[2 * LD + 2];
+  double S00 = r0p[p0], S10 = r0p[LD + p0], S20 = r0p[2 * LD + p0], S11 = r0p[LD + p0 + 1], S21 = r0p[2 * LD + p0 + 1],
+         S22 = r0p[2 * LD + p0 + 2];
   if (st.r_mode == 1) {
     S00 += Rdg[0]; S11 += Rdg[1]; S22 += Rdg[2];
   } else {
@@ -375,6 +360,7 @@ __device__ __forceinline__ void g_meas3(const Ctx<G, DC>& cx, const StreamDesc& 
     S00 += __ldg(Rm); S11 += __ldg(Rm + st.m + 1); S22 += __ldg(Rm + 2 * st.m + 2);
     S10 += __ldg(Rm + 1); S20 += __ldg(Rm + 2); S21 += __ldg(Rm + st.m + 2);
   }
+  __syncwarp();  // every lane has read the three rows before any lane overwrites its part of them
   const double d0 = S00, r0 = 1.0 / d0;
   const double l10 = S10 * r0, l20 = S20 * r0;
   const double d1 = fma(-l10 * l10, d0, S11), r1 = 1.0 / d1;
@@ -382,126 +368,117 @@ __device__ __forceinline__ void g_meas3(const Ctx<G, DC>& cx, const StreamDesc& 
   const double d2 = fma(-l21 * l21, d1, fma(-l20 * l20, d0, S22)), r2 = 1.0 / d2;
   const double pd = d0 * d1 * d2;
   const double logdet = (pd > 1e-290 && pd < 1e290) ? log(pd) : log(d0) + log(d1) + log(d2);
-  // Y = L^-1 HP for the lane's own columns, published in the scratch; wj = Y D^-1
+#pragma unroll
+  for (int c = 0; c < NA; c++) {
+    Y[1][c] = fma(-l10, Y[0][c], Y[1][c]);
+    Y[2][c] = fma(-l21, Y[1][c], fma(-l20, Y[0][c], Y[2][c]));
+  }
   double wj[NJ][3];
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    yo[j][1] = fma(-l10, yo[j][0], yo[j][1]);
-    yo[j][2] = fma(-l21, yo[j][1], fma(-l20, yo[j][0], yo[j][2]));
-    wj[j][0] = yo[j][0] * r0; wj[j][1] = yo[j][1] * r1; wj[j][2] = yo[j][2] * r2;
-    if (cx.template own<j>()) {
-      double* y = cx.Ys + 4 * cx.c[j];
-      *reinterpret_cast<double2*>(y) = make_double2(yo[j][0], yo[j][1]);
-      y[2] = yo[j][2];
-    }
-  });
-  __syncwarp();  // Y is complete, and every lane has read its part of the three rows before any lane overwrites them
-  g_sweep<G, DC, 3>(cx, wj);
-#ifdef RBIS_GROUP_COVONLY
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const double y1 = fma(-l10, yo[j][0], yo[j][1]);
+    const double y2 = fma(-l21, y1, fma(-l20, yo[j][0], yo[j][2]));
+    wj[j][0] = yo[j][0] * r0; wj[j][1] = y1 * r1; wj[j][2] = y2 * r2;
+  }
+  g_sweep<G, DC, 3>(Pf, w, Y, wj);
   __syncwarp();
+#ifdef RBIS_GROUP_COVONLY
+  s.ll += logdet + z[0] + z[1] + z[2] + Y[0][3] + Y[1][7] + Y[2][11];
   return;
 #endif
   double r[3];
   if (I0 == 6 && st.has_orient) {
-    r[0] = dquat.x - (cx.xs[6] - chi0.x); r[1] = dquat.y - (cx.xs[7] - chi0.y); r[2] = dquat.z - (cx.xs[8] - chi0.z);
+    r[0] = dquat.x - (s.x[6] - chi0.x); r[1] = dquat.y - (s.x[7] - chi0.y); r[2] = dquat.z - (s.x[8] - chi0.z);
   } else {
-    r[0] = z[0] - cx.xs[I0]; r[1] = z[1] - cx.xs[I0 + 1]; r[2] = z[2] - cx.xs[I0 + 2];
+    r[0] = z[0] - pick_triple<0>(s.x, I0); r[1] = z[1] - pick_triple<1>(s.x, I0); r[2] = z[2] - pick_triple<2>(s.x, I0);
   }
   const double e0 = r[0], e1 = fma(-l10, e0, r[1]), e2 = fma(-l21, e1, fma(-l20, e0, r[2]));
   const double u0 = e0 * r0, u1 = e1 * r1, u2 = e2 * r2;
-  double xn[NJ];
-  const double lln = cx.xs[XS_LL] + (-logdet - fma(e2, u2, fma(e1, u1, e0 * u0)));
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    xn[j] = fma(yo[j][0], u0, fma(yo[j][1], u1, fma(yo[j][2], u2, cx.xs[idx_of_rt<DC>(cx.c[j])])));
+  static_for<NA>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int xc = idx_of<DC>(c);
+    s.x[xc] = fma(Y[0][c], u0, fma(Y[1][c], u1, fma(Y[2][c], u2, s.x[xc])));
   });
-  __syncwarp();  // every lane has read the state it needs (the residual) before the owners update their components
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    if (cx.template own<j>()) cx.xs[idx_of_rt<DC>(cx.c[j])] = xn[j];
-  });
-  if (cx.l == 0) cx.xs[XS_LL] = lln;
-  __syncwarp();
+  s.ll += -logdet - fma(e2, u2, fma(e1, u1, e0 * u0));
 }
 
 // One-row chunk on state index idx (rbisk::meas1).
 template <int G, bool DC, bool SYN>
-__device__ __forceinline__ void g_meas1(const Ctx<G, DC>& cx, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int idx,
+__device__ __forceinline__ void g_meas1(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int idx,
                                         long long row, long long N, long long n, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
-  constexpr int LD = GE::LD, NJ = GE::NJ;
+  constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
   const double z = src.z(st, row, a0, sn);
   const double Rv = (st.r_mode == 1) ? ldg_early(st.R + (long long)a0 * N + n) : __ldg(st.R + a0 + (long long)st.m * a0);
+  const Own<G, NA> w(l);
   const int pi = pos_of<DC>(idx);
-  const double* rp = cx.Pf + pi * LD;
-  double ho[NJ], wj[NJ][1];
+  const double* rp = Pf + pi * LD;
+  double h[1][NA];
 #pragma unroll
-  for (int j = 0; j < NJ; j++) ho[j] = rp[cx.c[j]];
+  for (int k = 0; k < NA; k++) h[0][k] = rp[k];
+  double wj[NJ][1];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) wj[j][0] = rp[w.c[j]];
   const double sv = Rv + rp[pi];
-  const double r = 1.0 / sv;
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    wj[j][0] = ho[j] * r;
-    if (cx.template own<j>()) cx.Ys[4 * cx.c[j]] = ho[j];
-  });
   __syncwarp();
-  g_sweep<G, DC, 1>(cx, wj);
+  const double r = 1.0 / sv;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) wj[j][0] *= r;
+  g_sweep<G, DC, 1>(Pf, w, h, wj);
+  __syncwarp();
   double rr;
   if (st.has_orient && idx >= 6 && idx <= 8) {
     const int k = idx - 6;
     const double dq = (k == 0) ? dquat.x : (k == 1) ? dquat.y : dquat.z;
     const double c0 = (k == 0) ? chi0.x : (k == 1) ? chi0.y : chi0.z;
-    rr = dq - (cx.xs[idx] - c0);
+    rr = dq - (pick_state(s.x, idx) - c0);
   } else {
-    rr = z - cx.xs[idx];
+    rr = z - pick_state(s.x, idx);
   }
   const double u = rr * r;
-  double xn[NJ];
-  const double lln = cx.xs[XS_LL] + (-log(sv) - rr * u);
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    xn[j] = fma(ho[j], u, cx.xs[idx_of_rt<DC>(cx.c[j])]);
+  static_for<NA>([&](auto cc) {
+    constexpr int c = cc;
+    constexpr int xc = idx_of<DC>(c);
+    s.x[xc] = fma(h[0][c], u, s.x[xc]);
   });
-  __syncwarp();
-  static_for<NJ>([&](auto jc) {
-    constexpr int j = jc;
-    if (cx.template own<j>()) cx.xs[idx_of_rt<DC>(cx.c[j])] = xn[j];
-  });
-  if (cx.l == 0) cx.xs[XS_LL] = lln;
-  __syncwarp();
+  s.ll += -log(sv) - rr * u;
 }
 
 // A chunk of M correlated rows, decorrelated by the host (rbisk::meas_block): M scalar updates with rows
 // H'_a = sum_{b<=a} w_ab H_b and noise D_a.
 template <int G, bool DC, bool SYN>
-__device__ __forceinline__ void g_meas_block(const Ctx<G, DC>& cx, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int M,
+__device__ __forceinline__ void g_meas_block(double* Pf, const int l, FilterState& s, const StreamDesc& st, const MeasSrc<SYN>& src, int a0, int M,
                                              long long row, long long sn, const V3& dquat, const V3& chi0) {
   using GE = Geo<G, DC>;
-  constexpr int LD = GE::LD, NJ = GE::NJ;
+  constexpr int NA = GE::NA, LD = GE::LD, NJ = GE::NJ;
   const double* W = st.R + RS_W;
   const double* Dg = st.R + RS_D;
+  const Own<G, NA> w(l);
   for (int a = 0; a < M; a++) {
-    // the lane's own components of g = P H'_a^T, published in the scratch (every lane needs g at the measured indices)
-    double go[NJ], wj[NJ][1];
+    double g[1][NA];
+    double wj[NJ][1];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) go[j] = 0.0;
+    for (int k = 0; k < NA; k++) g[0][k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) wj[j][0] = 0.0;
     for (int b = 0; b <= a; b++) {
       const double wt = __ldg(W + (a0 + a) * MAX_MEAS + (a0 + b));
-      const double* rp = cx.Pf + pos_of<DC>(st.idx[a0 + b]) * LD;
+      const double* rp = Pf + pos_of<DC>(st.idx[a0 + b]) * LD;
 #pragma unroll
-      for (int j = 0; j < NJ; j++) go[j] = fma(wt, rp[cx.c[j]], go[j]);
+      for (int k = 0; k < NA; k++) g[0][k] = fma(wt, rp[k], g[0][k]);
+#pragma unroll
+      for (int j = 0; j < NJ; j++) wj[j][0] = fma(wt, rp[w.c[j]], wj[j][0]);  // the lane's own g[c_j], bitwise equal to g[0][c_j]
     }
-    static_for<NJ>([&](auto jc) {
-      constexpr int j = jc;
-      if (cx.template own<j>()) cx.Ys[4 * cx.c[j]] = go[j];
-    });
-    __syncwarp();
     double sv = __ldg(Dg + a0 + a), rp_ = 0.0;
     for (int b = 0; b <= a; b++) {
       const double wt = __ldg(W + (a0 + a) * MAX_MEAS + (a0 + b));
       const int ib = st.idx[a0 + b];
-      sv = fma(wt, cx.Ys[4 * pos_of<DC>(ib)], sv);
-      const double xi = cx.xs[ib];
+      const int pb = pos_of<DC>(ib);
+      double gi = g[0][0];
+#pragma unroll
+      for (int k = 1; k < NA; k++) gi = (pb == k) ? g[0][k] : gi;
+      sv = fma(wt, gi, sv);
+      const double xi = pick_state(s.x, ib);
       double rb;
       if (st.has_orient && ib >= 6 && ib <= 8) {
         const int k = ib - 6;
@@ -513,24 +490,19 @@ __device__ __forceinline__ void g_meas_block(const Ctx<G, DC>& cx, const StreamD
       }
       rp_ = fma(wt, rb, rp_);
     }
+    __syncwarp();
     const double r = 1.0 / sv;
 #pragma unroll
-    for (int j = 0; j < NJ; j++) wj[j][0] = go[j] * r;
-    g_sweep<G, DC, 1>(cx, wj);
-    const double u = rp_ * r;
-    double xn[NJ];
-    const double lln = cx.xs[XS_LL] + (-log(sv) - rp_ * u);
-    static_for<NJ>([&](auto jc) {
-      constexpr int j = jc;
-      xn[j] = fma(go[j], u, cx.xs[idx_of_rt<DC>(cx.c[j])]);
-    });
-    __syncwarp();  // the sweep and the state reads of every lane are done: Y scratch and state may change
-    static_for<NJ>([&](auto jc) {
-      constexpr int j = jc;
-      if (cx.template own<j>()) cx.xs[idx_of_rt<DC>(cx.c[j])] = xn[j];
-    });
-    if (cx.l == 0) cx.xs[XS_LL] = lln;
+    for (int j = 0; j < NJ; j++) wj[j][0] *= r;
+    g_sweep<G, DC, 1>(Pf, w, g, wj);
     __syncwarp();
+    const double u = rp_ * r;
+    static_for<NA>([&](auto cc) {
+      constexpr int c = cc;
+      constexpr int xc = idx_of<DC>(c);
+      s.x[xc] = fma(g[0][c], u, s.x[xc]);
+    });
+    s.ll += -log(sv) - rp_ * u;
   }
 }
 
@@ -580,28 +552,12 @@ __device__ __forceinline__ void g_cov_store(const double* Pf, const int l, doubl
     }
   }
 }
-// state block <-> [21][stride] vec, [4][stride] quat, loglik, split over the lanes of the group
-template <int G>
-__device__ __forceinline__ void g_state_load(double* xs, const int l, const double* __restrict__ vec, const double* __restrict__ quat,
-                                             const double* __restrict__ ll, long long stride) {
-  for (int k = l; k < XS_QN; k += G) xs[k] = k < NS ? vec[(long long)k * stride] : (k < XS_LL ? quat[(long long)(k - NS) * stride] : ll[0]);
-}
-template <int G>
-__device__ __forceinline__ void g_state_store(const double* xs, const int l, double* __restrict__ vec, double* __restrict__ quat,
-                                              double* __restrict__ ll, long long stride, bool active) {
-  if (!active) return;
-  for (int k = l; k < XS_QN; k += G) {
-    if (k < NS) vec[(long long)k * stride] = xs[k];
-    else if (k < XS_LL) quat[(long long)(k - NS) * stride] = xs[k];
-    else ll[0] = xs[k];
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // The fused kernel, warp-group mapping.  Same parameter block, op program and semantics as rbisk::rbis_fused_kernel;
 // all chunk kinds (aligned triples, one-row chunks, correlated blocks) are compiled in (the indices are run-time
 // shared-memory addresses here, so the general paths cost the common program nothing).
-// MAXW = warps per CTA the launch may use (register budget: 8 -> 255 registers, 14 -> 144, 16 -> 128).
+// MAXW = warps per CTA the launch may use (register budget: 8 -> 255 registers, 16 -> 128).
 // ------------------------------------------------------------------------------------------------
 // SYN = true: input rows drawn inside the kernel (KParams::syn), as in rbisk::rbis_fused_kernel.
 template <int G, bool DC, int MAXW, bool SYN = false>
@@ -617,15 +573,14 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
   long long n = (((long long)blockIdx.x + p.block_offset) * wpc + warp) * FPW + lane / G;
   const bool active = n < N;
   if (!active) n = N - 1;  // idle groups shadow the last filter and never store
-  const Ctx<G, DC> cx(smem + (size_t)(warp * FPW + lane / G) * S, l);
-  double* const xs = cx.xs;
+  const bool writer = active && l == 0;
+  double* Pf = smem + (size_t)(warp * FPW + lane / G) * S;
 
-  g_state_load<G>(xs, l, p.vec + n, p.quat + n, p.loglik + n, N);
-  if (l == 0) {
-    xs[XS_QN] = __ldg(p.q_gyro + n); xs[XS_QN + 1] = __ldg(p.q_accel + n);
-    xs[XS_QN + 2] = __ldg(p.q_gyro_bias + n); xs[XS_QN + 3] = __ldg(p.q_accel_bias + n);
-  }
-  g_cov_load<G, DC>(cx.Pf, l, p.P + n, N);  // ends with __syncwarp()
+  FilterState s;
+  static_for<NS>([&](auto i) { s.x[i] = p.vec[(long long)i * N + n]; });
+  s.qw = p.quat[n]; s.qx = p.quat[N + n]; s.qy = p.quat[2 * N + n]; s.qz = p.quat[3 * N + n];
+  s.ll = p.loglik[n];
+  g_cov_load<G, DC>(Pf, l, p.P + n, N);
   bool imu_seen = false;  // DC: an IMU step ran since the (omega,omega) / (a,a) blocks in p.P were current
 
   auto load_op = [&](long long i) {
@@ -638,9 +593,12 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
     return o;
   };
   const long long imu_n = p.imu_map ? (long long)__ldg(p.imu_map + n) : n;
+  QNoise qn;
+  qn.q_gyro = __ldg(p.q_gyro + n); qn.q_accel = __ldg(p.q_accel + n);
+  qn.q_gyro_bias = __ldg(p.q_gyro_bias + n); qn.q_accel_bias = __ldg(p.q_accel_bias + n);
 
   // Ops are fetched two ahead, and the INPUT ROWS of the next op are prefetched into L1 while the current op runs: with
-  // few warps per scheduler nothing else hides the latency of a first touch of HBM.
+  // one or two warps per scheduler nothing else hides the latency of a first touch of HBM.
   auto prefetch = [&](const double* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
   unsigned long long syn_kf = 0;
   double syn_sg = 0.0, syn_sa = 0.0;
@@ -666,7 +624,6 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
       }
     }
   };
-  auto load_quat = [&]() { return Q4{xs[XS_Q], xs[XS_Q + 1], xs[XS_Q + 2], xs[XS_Q + 3]}; };
   Op op1 = load_op(0);
   Op op2 = p.n_ops > 1 ? load_op(1) : op1;
   for (long long oi = 0; oi < p.n_ops; oi++) {
@@ -693,7 +650,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
         acc = {ldg_early(base + 3 * Ni), ldg_early(base + 4 * Ni), ldg_early(base + 5 * Ni)};
       }
       const double dt = op.dt;
-      const Q4 q = load_quat();
+      const Q4 q{s.qw, s.qx, s.qy, s.qz};
       const double tx_ = 2 * q.x, ty_ = 2 * q.y, tz_ = 2 * q.z;
       const double twx_ = tx_ * q.w, twy_ = ty_ * q.w, twz_ = tz_ * q.w;
       const double txx_ = tx_ * q.x, txy_ = ty_ * q.x, txz_ = tz_ * q.x;
@@ -703,39 +660,29 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
       const double R20 = txz_ - twy_, R21 = tyz_ + twx_, R22 = 1 - (txx_ + tyy_);
       const V3 gb{-p.g_val * R20, -p.g_val * R21, -p.g_val * R22};
       Lin L;
-      L.v = {xs[3], xs[4], xs[5]};
-      L.wd = {xs[0] * dt, xs[1] * dt, xs[2] * dt};  // omega of the PRIOR state (rbis_update_interface.cpp:38-39)
+      L.v = {s.x[3], s.x[4], s.x[5]};
+      L.wd = {s.x[0] * dt, s.x[1] * dt, s.x[2] * dt};  // omega of the PRIOR state (rbis_update_interface.cpp:38-39)
       L.vd = {L.v.x * dt, L.v.y * dt, L.v.z * dt};
       L.gd = {gb.x * dt, gb.y * dt, gb.z * dt};
       L.dt = dt;
       L.Rd[0] = R00 * dt; L.Rd[1] = R01 * dt; L.Rd[2] = R02 * dt;
       L.Rd[3] = R10 * dt; L.Rd[4] = R11 * dt; L.Rd[5] = R12 * dt;
       L.Rd[6] = R20 * dt; L.Rd[7] = R21 * dt; L.Rd[8] = R22 * dt;
-      if (l == 0) {
-        const double vx = L.v.x, vy = L.v.y, vz = L.v.z;
-        xs[9] += fma(R02, vz, fma(R01, vy, R00 * vx)) * dt;
-        xs[10] += fma(R12, vz, fma(R11, vy, R10 * vx)) * dt;
-        xs[11] += fma(R22, vz, fma(R21, vy, R20 * vx)) * dt;
+      {
+        const double vx = s.x[3], vy = s.x[4], vz = s.x[5];
+        s.x[9] += fma(R02, vz, fma(R01, vy, R00 * vx)) * dt;
+        s.x[10] += fma(R12, vz, fma(R11, vy, R10 * vx)) * dt;
+        s.x[11] += fma(R22, vz, fma(R21, vy, R20 * vx)) * dt;
       }
       imu_seen = true;
-      const QNoise qn{xs[XS_QN], xs[XS_QN + 1], xs[XS_QN + 2], xs[XS_QN + 3]};
-      g_cov_propagate<G, DC>(cx, L, qn);
-#if !defined(RBIS_GROUP_COVONLY)
-      {
-        // insUpdateState from the shared copy (the position was advanced above): every lane evaluates it, lane 0 stores
-        FilterState s;
-        static_for<9>([&](auto i) { s.x[i] = xs[i]; });
-        static_for<6>([&](auto i) { s.x[15 + i] = xs[15 + i]; });
-        s.qw = q.w; s.qx = q.x; s.qy = q.y; s.qz = q.z;
-        state_propagate<true>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
-        __syncwarp();
-        if (l == 0) {
-          static_for<9>([&](auto i) { xs[i] = s.x[i]; });
-          static_for<3>([&](auto i) { xs[12 + i] = s.x[12 + i]; });
-          xs[XS_Q] = s.qw; xs[XS_Q + 1] = s.qx; xs[XS_Q + 2] = s.qy; xs[XS_Q + 3] = s.qz;
-        }
-        __syncwarp();
-      }
+      // the state step only needs the prior state (already captured in L): issued first, its long dependent chain
+      // (rsqrt, sin / cos, quaternion product) overlaps the covariance passes
+#if RBIS_GROUP_STATE_FIRST && !defined(RBIS_GROUP_COVONLY)
+      state_propagate<true>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
+#endif
+      g_cov_propagate<G, DC>(Pf, l, L, qn);
+#if !RBIS_GROUP_STATE_FIRST && !defined(RBIS_GROUP_COVONLY)
+      state_propagate<true>(s, gyro, acc, dt, gb, p.chi_tol, p.renorm);
 #endif
     } else if (op.kind == 1) {
       // ---- indexed / indexed-plus-orientation measurement ----
@@ -747,53 +694,47 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
         src.kfs = syn_kf ^ ((unsigned long long)__ldg(src.ss->step + op.row) * SYN_K2);
       }
       V3 dquat{0, 0, 0};
-      if (st.has_orient) dquat = subtract_quats(src.quat(st, op.row, sn), load_quat());  // rbis.cpp:199
-      const V3 chi0{xs[6], xs[7], xs[8]};
+      if (st.has_orient) dquat = subtract_quats(src.quat(st, op.row, sn), {s.qw, s.qx, s.qy, s.qz});  // rbis.cpp:199
+      const V3 chi0{s.x[6], s.x[7], s.x[8]};
       for (int ci = 0; ci < st.n_chunks; ci++) {
         const int a0 = st.chunk_start[ci];
         const int fast = st.chunk_fast[ci];
-        if (fast >= 0 && fast < 100) g_meas3<G, DC>(cx, st, src, a0, fast, op.row, N, n, sn, dquat, chi0);
-        else if (fast >= 100) g_meas1<G, DC>(cx, st, src, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
-        else g_meas_block<G, DC>(cx, st, src, a0, st.chunk_len[ci], op.row, sn, dquat, chi0);
+        if (fast >= 0 && fast < 100) g_meas3<G, DC>(Pf, l, s, st, src, a0, fast, op.row, N, n, sn, dquat, chi0);
+        else if (fast >= 100) g_meas1<G, DC>(Pf, l, s, st, src, a0, fast - 100, op.row, N, n, sn, dquat, chi0);
+        else g_meas_block<G, DC>(Pf, l, s, st, src, a0, st.chunk_len[ci], op.row, sn, dquat, chi0);
       }
 #ifndef RBIS_GROUP_COVONLY
-      {
-        FilterState s;
-        s.x[6] = xs[6]; s.x[7] = xs[7]; s.x[8] = xs[8];
-        const Q4 q = load_quat();
-        s.qw = q.w; s.qx = q.x; s.qy = q.y; s.qz = q.z;
-        meas_finish(s, chi0, p.chi_tol, p.ctor_folds_chi, p.renorm);
-        __syncwarp();
-        if (l == 0) {
-          xs[6] = s.x[6]; xs[7] = s.x[7]; xs[8] = s.x[8];
-          xs[XS_Q] = s.qw; xs[XS_Q + 1] = s.qx; xs[XS_Q + 2] = s.qy; xs[XS_Q + 3] = s.qz;
-        }
-        __syncwarp();
-      }
+      meas_finish(s, chi0, p.chi_tol, p.ctor_folds_chi, p.renorm);
 #endif
     } else if (op.kind == 2) {
       // ---- snapshot into ring slot ----
       double* d = p.snap + op.row * SNAP_ROWS * N + n;
-      g_state_store<G>(xs, l, d, d + 21 * N, d + 25 * N, N, active);
+      if (writer) {
+        static_for<NS>([&](auto i) { d[(long long)i * N] = s.x[i]; });
+        d[21 * N] = s.qw; d[22 * N] = s.qx; d[23 * N] = s.qy; d[24 * N] = s.qz;
+        d[25 * N] = s.ll;
+      }
       double* dc = d + 26 * N;
-      g_cov_store<G, DC>(cx.Pf, l, dc, N, active);
+      g_cov_store<G, DC>(Pf, l, dc, N, active);
       if constexpr (DC) {
         if (active) {
           for (int k = l; k < N_REST; k += G) dc[(long long)c_act.rest[k] * N] = 0.0;
           for (int k = l; k < 12; k += G) {
             const int s_ = c_act.blk[k];
             const int jc = col_of_slot(s_), ir = s_ - jc * (jc + 1) / 2;
-            dc[(long long)s_ * N] = imu_seen ? ((ir != jc) ? 0.0 : (jc < 3 ? xs[XS_QN] : xs[XS_QN + 1])) : p.P[(long long)s_ * N + n];
+            dc[(long long)s_ * N] = imu_seen ? ((ir != jc) ? 0.0 : (jc < 3 ? qn.q_gyro : qn.q_accel)) : p.P[(long long)s_ * N + n];
           }
         }
       }
     } else {
       // ---- restore from ring slot ----
       const double* d = p.snap + op.row * SNAP_ROWS * N + n;
-      __syncwarp();
-      g_state_load<G>(xs, l, d, d + 21 * N, d + 25 * N, N);
+      static_for<NS>([&](auto i) { s.x[i] = d[(long long)i * N]; });
+      s.qw = d[21 * N]; s.qx = d[22 * N]; s.qy = d[23 * N]; s.qz = d[24 * N];
+      s.ll = d[25 * N];
       const double* dc = d + 26 * N;
-      g_cov_load<G, DC>(cx.Pf, l, dc, N);  // ends with __syncwarp()
+      __syncwarp();
+      g_cov_load<G, DC>(Pf, l, dc, N);
       if constexpr (DC) {
         // the slot's (omega,omega) / (a,a) blocks become the current ones: parked in p.P (this filter's own column)
         if (active)
@@ -806,14 +747,18 @@ __global__ void __launch_bounds__(32 * MAXW, 1) rbis_group_kernel(const __grid_c
     }
   }
 
-  g_state_store<G>(xs, l, p.vec + n, p.quat + n, p.loglik + n, N, active);
-  g_cov_store<G, DC>(cx.Pf, l, p.P + n, N, active);
+  if (writer) {
+    static_for<NS>([&](auto i) { p.vec[(long long)i * N + n] = s.x[i]; });
+    p.quat[n] = s.qw; p.quat[N + n] = s.qx; p.quat[2 * N + n] = s.qy; p.quat[3 * N + n] = s.qz;
+    p.loglik[n] = s.ll;
+  }
+  g_cov_store<G, DC>(Pf, l, p.P + n, N, active);
   if constexpr (DC) {
     if (active && imu_seen)
       for (int k = l; k < 12; k += G) {
         const int s_ = c_act.blk[k];
         const int jc = col_of_slot(s_), ir = s_ - jc * (jc + 1) / 2;
-        p.P[(long long)s_ * N + n] = (ir != jc) ? 0.0 : (jc < 3 ? xs[XS_QN] : xs[XS_QN + 1]);
+        p.P[(long long)s_ * N + n] = (ir != jc) ? 0.0 : (jc < 3 ? qn.q_gyro : qn.q_accel);
       }
   }
 }
