@@ -267,7 +267,16 @@ int rbis_batch_run_fused_synth(rbis_batch_t* h, int64_t n_ops, const rbis_op_t* 
  * update stamped u), plus one at the start.  Updates older than the oldest retained history entry are
  * discarded as in update_history.cpp:28-39; so are updates that no retained snapshot precedes.
  * History is truncated to `history_span_us` behind the newest update after every roll-forward
- * (mav_state_est.cpp:74-77).  Host-side only; no device work. */
+ * (mav_state_est.cpp:74-77).  The rewind window is therefore ~ snapshot_slots x snapshot_period_us: choose them so that it
+ * covers history_span_us when every update the reference would replay must be replayed (rbis_planner_create leaves a
+ * warning in rbis_last_error() when it does not; the C++ shim's default does).  Host-side only; no device work.
+ *
+ * ONE SCHEDULE PER HANDLE.  A planner serves one rbis_batch_t: all of its filters see the same arrivals in the same order --
+ * the shape of every workload in BASELINE.json (a noise sweep or a parameter sweep replays ONE log; delayed pose fixes are
+ * late for every realisation alike).  Filters whose measurements arrive on DIFFERENT schedules belong in different handles,
+ * one planner each: handles are independent (own streams, own snapshot ring), their launches run concurrently on the device,
+ * and the warp-group kernels keep small sub-ensembles efficient; tests/test_gpu_parity.py
+ * (test_two_arrival_schedules_as_two_handles) runs two schedules side by side against the oracle's per-filter histories. */
 typedef struct rbis_planner rbis_planner_t;
 int rbis_planner_create(rbis_planner_t** out, int64_t utime0, int32_t snapshot_slots, int64_t snapshot_period_us,
                         int64_t snapshot_phase_us, int64_t history_span_us);

@@ -210,11 +210,18 @@ class MavStateEstimator {
  public:
   int64_t utime_history_span;
 
+  // snapshot_period_us = 0 (default): chosen so that the snapshot ring covers the whole history span (slots x period >=
+  // utime_history_span, whole milliseconds), i.e. every update the reference would still replay (update_history.cpp:28-39) can be
+  // rewound to; an explicit, shorter period trades a shorter rewind window for shorter replays (rbis_planner_create).
   MavStateEstimator(int64_t n_filters, RBISResetUpdate* init_state, int64_t utime_history_span_us, int32_t snapshot_slots = 4,
-                    int64_t snapshot_period_us = 50000, const rbis_batch_config_t* cfg = nullptr)
+                    int64_t snapshot_period_us = 0, const rbis_batch_config_t* cfg = nullptr)
       : utime_history_span(utime_history_span_us), filters_(make_ensemble(n_filters, snapshot_slots, cfg)) {
     std::unique_ptr<RBISResetUpdate> init(init_state);
     init->updateFilter(*filters_);  // MSE/mav_state_est.cpp:16
+    if (snapshot_period_us <= 0 && snapshot_slots > 0) {
+      const int64_t per = (utime_history_span_us + snapshot_slots - 1) / snapshot_slots;
+      snapshot_period_us = std::max<int64_t>(1000, (per + 999) / 1000 * 1000);
+    }
     check(rbis_planner_create(&planner_, init->utime, snapshot_slots, snapshot_period_us, init->utime, utime_history_span_us));
   }
   ~MavStateEstimator() { rbis_planner_destroy(planner_); }

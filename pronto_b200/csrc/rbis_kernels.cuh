@@ -87,6 +87,10 @@
 #ifndef RBIS_STAGGER_NS
 #define RBIS_STAGGER_NS 0
 #endif
+#ifndef RBIS_UNIFORM_WARP
+#define RBIS_UNIFORM_WARP 0  // 1: warp index broadcast from lane 0, so that the tensor-memory base lives in a uniform register (SASS: 389 -> 17
+                             // R2UR, +133 MOV; measured -1 %: dev knob, off)
+#endif
 #ifndef RBIS_SWEEP_TILE
 #define RBIS_SWEEP_TILE 8  // slots per pipelined tile of the measurement covariance sweep
 #endif
@@ -1461,7 +1465,13 @@ __global__ void __launch_bounds__(TPB, 1) rbis_fused_kernel(const __grid_constan
   extern __shared__ __align__(16) double smem[];
   __shared__ uint32_t tm_base_s;
   const int tid = threadIdx.x;
+#if RBIS_UNIFORM_WARP
+  // broadcast from lane 0: the compiler then knows the warp index (and the tensor-memory base derived from it) is warp
+  // uniform and keeps it in a uniform register, which is what tcgen05.ld / st take as their address
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#else
   const int warp = tid >> 5;
+#endif
   // ---- tensor memory: all 512 columns; warp w owns lanes 32*(w%4).. and columns TM_COLS*(w/4).. ----
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_s)) : "memory");

@@ -149,6 +149,13 @@ int rbis_planner_create(rbis_planner_t** out, int64_t utime0, int32_t snapshot_s
   for (int32_t s = snapshot_slots - 1; s >= 0; s--) p->free_slots.push_back(s);
   p->counters[5] = 1;
   *out = p;
+  // An update can only be rewound to while a snapshot at or before it is retained, i.e. within ~ slots x period of the head;
+  // the reference replays anything newer than the oldest history entry (the whole span).  Not an error -- a shorter window buys
+  // shorter replays -- but the caller should know: the text is left in rbis_last_error().
+  if (history_span_us > 0 && (int64_t)snapshot_slots * snapshot_period_us < history_span_us)
+    rbis_set_error(0, "rbis_planner_create: rewind window %lld us (snapshot_slots x snapshot_period_us) is shorter than history_span_us %lld: "
+                      "updates delayed beyond it are discarded where the reference would replay them",
+                   (long long)((int64_t)snapshot_slots * snapshot_period_us), (long long)history_span_us);
   return 0;
 }
 

@@ -298,6 +298,64 @@ def test_delayed_pose_fix_rewind_matches_oracle_history(oracle):
     assert n_applied * N == ref["calls"]  # the device re-applies exactly what the reference's replay re-applies
 
 
+def test_two_arrival_schedules_as_two_handles(oracle):
+    """Filters whose measurements arrive on different schedules live in different handles, one planner each (rbis_batch.h,
+    "one schedule per handle"): sub-ensemble A gets its pose fixes 50 steps late, B 20 steps late and its leg odometry 3 steps
+    late; the two handles are driven chunk by chunk, interleaved on the device, and each must match the oracle's per-filter
+    multimap history fed with ITS arrivals."""
+    from pronto_b200.schedule import program_from_arrivals
+
+    N, T = 64, 300
+    sc = scenario(N, T)
+    st = sc["st"]
+    ev = st["events"]
+
+    def delayed(lat_pose, lat_lego):
+        out, pend = [], []
+        for e in ev:
+            lat = 0 if e[0] == 0 else (lat_pose if e[1] == 1 else lat_lego)
+            if e[0] == 0 or lat == 0:
+                out.append(e)
+            else:
+                pend.append((e[3] + lat * 1000, e))
+            if e[0] == 0:
+                due = [q for q in pend if q[0] <= e[3]]
+                pend = [q for q in pend if q[0] > e[3]]
+                out += [q[1] for q in due]
+        return out + [q[1] for q in pend]
+
+    halves = {"A": (0, N // 2, delayed(50, 0)), "B": (N // 2, N, delayed(20, 3))}
+    sub = lambda a, lo, hi: np.ascontiguousarray(a[..., lo:hi])
+    handles, progs = {}, {}
+    try:
+        for name, (lo, hi, arr) in halves.items():
+            ops, cnt = program_from_arrivals(arr, snapshot_slots=4, snapshot_period_us=25_000, snapshot_phase_us=1000)
+            assert cnt["discarded"] == 0 and cnt["rewinds"] > 0
+            b = RBISBatch(hi - lo, snapshot_slots=4)
+            b.set_process_noise(*nominal_q())
+            b.set_state(sub(sc["vec"], lo, hi), sub(sc["quat"], lo, hi), sub(sc["cov"], lo, hi))
+            handles[name], progs[name] = b, ops
+        # interleaved launches of the two programs, cut at arbitrary places (pieces of one handle run in order on its stream)
+        cuts = {k: np.linspace(0, len(v), 5).astype(int) for k, v in progs.items()}
+        for i in range(4):
+            for name, (lo, hi, _) in halves.items():
+                piece = progs[name][cuts[name][i]:cuts[name][i + 1]]
+                handles[name].run_fused(piece, imu=sub(st["imu"], lo, hi),
+                                        streams=[MeasStream(synth.LEGODO_IDX, sub(st["legodo"], lo, hi), st["R_legodo"]),
+                                                 MeasStream(synth.POSE_IDX, sub(st["pose_z"], lo, hi), st["R_pose"], quat=sub(st["pose_q"], lo, hi))])
+        for name, (lo, hi, arr) in halves.items():
+            gv, gq, gP, gll, _ = handles[name].get_state()
+            ost = [dict(idx=synth.LEGODO_IDX, z=sub(st["legodo"], lo, hi), R=st["R_legodo"]),
+                   dict(idx=synth.POSE_IDX, z=sub(st["pose_z"], lo, hi), R=st["R_pose"], quat=sub(st["pose_q"], lo, hi))]
+            ref = oracle.run_ensemble(sub(sc["vec"], lo, hi), sub(sc["quat"], lo, hi), sub(sc["cov"], lo, hi), None, 0, nominal_q(),
+                                      sub(st["imu"], lo, hi), ost, arr, n_threads=NTHREADS)
+            _assert_close((gv, gq, gP), (ref["vec"], ref["quat"], ref["cov"]), STEP_TOL, f"schedule {name}")
+            assert _rel_ll(gll, ref["loglik"]) < STEP_TOL
+    finally:
+        for b in handles.values():
+            b.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # statistics
 # ------------------------------------------------------------------------------------------------
