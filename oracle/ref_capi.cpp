@@ -15,6 +15,7 @@
 #include <estimate_tools/imu_stream.hpp>
 #include <list>
 #include <noise_id/noise_id.hpp>          // -I /root/reference/state-estimator/src
+#include <mav_est_legodo/rbis_legodo_common.hpp>  // -I /root/reference/motion_estimate/src
 #include "mav_state_est.hpp"  // the reference's headers, found with -I /root/reference/state-estimator/src/mav_state_est
 
 extern "C" int64_t rbis_ref_shim_history_span = 10000000;  // what the BotParam stand-in returns (ref_shim/bot_param)
@@ -338,3 +339,49 @@ int orc_kvh_decode(int64_t batch_utime, int n, const double* packets, double* ou
 }
 
 }  // extern "C"
+
+// ---- leg-odometry measurement formation: LegOdoCommon::createMeasurement (motion_estimate/src/mav_est_legodo/
+// rbis_legodo_common.cpp:110-170 with getCovariance :35-88 and pronto::getDeltaAsVelocity, pronto_conversions_lcm.hpp:38-87),
+// compiled unmodified.  The constructor's BotParam reads are served from these process-wide variables. ----
+extern "C" {
+const char* rbis_ref_shim_legodo_mode = "lin_rate";
+double rbis_ref_shim_legodo_r[5] = {0, 0, 0, 0, 0};
+char* rbis_ref_shim_param_str(const char* key) {
+  (void)key;  // the only string key is state_estimator.legodo.mode
+  return strdup(rbis_ref_shim_legodo_mode);
+}
+double rbis_ref_shim_param_double(const char* key) {
+  const char* names[5] = {"state_estimator.legodo.r_xyz", "state_estimator.legodo.r_vxyz", "state_estimator.legodo.r_vang",
+                          "state_estimator.legodo.r_vxyz_uncertain", "state_estimator.legodo.r_vang_uncertain"};
+  for (int k = 0; k < 5; k++)
+    if (!strcmp(key, names[k])) return rbis_ref_shim_legodo_r[k];
+  fprintf(stderr, "ref shim: unknown parameter %s\n", key);
+  abort();
+}
+// mode: "lin_rate" / "lin_rot_rate" / "pos_and_lin_rate"; r[5] as above; position / delta: translation xyz and quaternion wxyz.
+// Outputs: m, idx[m], z[m], cov[m*m] (column-major); returns the sensor id, or -1 when the reference returned NULL.
+int orc_legodo_create_measurement(const char* mode, const double* r, const double* pos_xyz, const double* pos_quat, const double* delta_xyz,
+                                  const double* delta_quat, int64_t utime, int64_t prev_utime, int odo_position_status, float odo_delta_status,
+                                  int* m_out, int* idx_out, double* z_out, double* cov_out, int64_t* utime_out) {
+  rbis_ref_shim_legodo_mode = mode;
+  for (int k = 0; k < 5; k++) rbis_ref_shim_legodo_r[k] = r[k];
+  std::streambuf* old = std::cout.rdbuf(nullptr);  // the constructor announces its mode on stdout
+  LegOdoCommon common(nullptr, nullptr, nullptr);
+  std::cout.rdbuf(old);
+  BotTrans posT, deltaT;
+  for (int k = 0; k < 3; k++) { posT.trans_vec[k] = pos_xyz[k]; deltaT.trans_vec[k] = delta_xyz[k]; }
+  for (int k = 0; k < 4; k++) { posT.rot_quat[k] = pos_quat[k]; deltaT.rot_quat[k] = delta_quat[k]; }
+  RBISUpdateInterface* u = common.createMeasurement(posT, deltaT, utime, prev_utime, odo_position_status, odo_delta_status);
+  if (!u) return -1;
+  RBISIndexedMeasurement* im = dynamic_cast<RBISIndexedMeasurement*>(u);
+  const int m = (int)im->index.rows();
+  *m_out = m;
+  for (int a = 0; a < m; a++) { idx_out[a] = im->index(a); z_out[a] = im->measurement(a); }
+  for (int b = 0; b < m; b++)
+    for (int a = 0; a < m; a++) cov_out[a + m * b] = im->measurement_cov(a, b);
+  *utime_out = u->utime;
+  const int sensor = (int)u->sensor_id;
+  delete u;
+  return sensor;
+}
+}

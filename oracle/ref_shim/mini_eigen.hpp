@@ -11,6 +11,8 @@
 #include <cstddef>
 #include <iostream>
 #include <type_traits>
+#include <sstream>
+#include <string>
 #include <vector>
 
 namespace Eigen {
@@ -250,6 +252,12 @@ class Matrix : public WritableBase<Matrix<T, R, C> > {
   const T* data() const { return d_.data(); }
   T& operator[](int i) { return d_[(size_t)i]; }   // vectors only
   const T& operator[](int i) const { return d_[(size_t)i]; }
+  T x() const { return d_[0]; }
+  T y() const { return d_[1]; }
+  T z() const { return d_[2]; }
+  T& x() { return d_[0]; }
+  T& y() { return d_[1]; }
+  T& z() { return d_[2]; }
 
   static Matrix Zero() { return Matrix(); }
   static Matrix Zero(int r, int c = 1) { return Matrix(r, c); }
@@ -557,6 +565,29 @@ class Quaternion {
  public:
   Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
   Quaternion(T w, T x, T y, T z) : w_(w), x_(x), y_(y), z_(z) {}
+  // from a rotation matrix: Eigen's quaternionbase_assign_impl<Matrix3> (trace branch, else the largest diagonal element)
+  explicit Quaternion(const Matrix<T, 3, 3>& m) {
+    T t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > T(0)) {
+      t = std::sqrt(t + T(1));
+      w_ = T(0.5) * t;
+      t = T(0.5) / t;
+      x_ = (m(2, 1) - m(1, 2)) * t; y_ = (m(0, 2) - m(2, 0)) * t; z_ = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1));
+      T v[3];
+      v[i] = T(0.5) * t;
+      t = T(0.5) / t;
+      w_ = (m(k, j) - m(j, k)) * t;
+      v[j] = (m(j, i) + m(i, j)) * t;
+      v[k] = (m(k, i) + m(i, k)) * t;
+      x_ = v[0]; y_ = v[1]; z_ = v[2];
+    }
+  }
   static Quaternion Identity() { return Quaternion(1, 0, 0, 0); }
   T w() const { return w_; }
   T x() const { return x_; }
@@ -634,7 +665,34 @@ class LLT {
 template <typename T, int R, int C>
 LLT<Matrix<T, R, C> > Matrix<T, R, C>::llt() const { return LLT<Matrix>(*this); }
 
+// ---- Transform<T, 3, Isometry>: rotation + translation, the few members pronto_conversions_* use ----
+template <typename T>
+class Isometry3 {
+ public:
+  Isometry3() { setIdentity(); }
+  void setIdentity() { R_.setIdentity(); t_ = Matrix<T, 3, 1>(); }
+  Matrix<T, 3, 1>& translation() { return t_; }
+  const Matrix<T, 3, 1>& translation() const { return t_; }
+  Matrix<T, 3, 3> rotation() const { return R_; }
+  Matrix<T, 3, 3>& linear() { return R_; }
+  const Matrix<T, 3, 3>& linear() const { return R_; }
+  Isometry3& rotate(const Quaternion<T>& q) {  // applies the rotation on the right of the current transform
+    R_ = R_ * q.toRotationMatrix();
+    return *this;
+  }
+
+ private:
+  Matrix<T, 3, 3> R_;
+  Matrix<T, 3, 1> t_;
+};
+typedef Isometry3<double> Isometry3d;
+typedef Isometry3<float> Isometry3f;
+#ifndef EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#endif
+
 template <class T> using aligned_allocator = std::allocator<T>;
+typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, Dynamic, 1> VectorXd;

@@ -139,3 +139,62 @@ def test_legodo_measurement_formation(rbis_lib, tmp_path):
                     np.arcsin(2 * (q[0] * q[2] - q[3] * q[1])),
                     np.arctan2(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] ** 2 + q[3] ** 2))])
     assert np.allclose(lr["z"], np.concatenate([(dxyz / 0.004).reshape(-1), (rpy / 0.004).reshape(-1)]), rtol=1e-14)
+
+
+def test_legodo_measurement_formation_matches_the_reference_compiled(rbis_lib):
+    """The same class against the reference's own LegOdoCommon::createMeasurement (rbis_legodo_common.cpp:35-170 with
+    pronto::getDeltaAsVelocity, pronto_conversions_lcm.hpp:38-87, and pronto_math.cpp), compiled unmodified into oracle/_ref:
+    index set, measurement covariance, measurement vector, utime and sensor id for random poses, all three modes, certain /
+    uncertain deltas, valid / invalid positions."""
+    import ctypes as C
+
+    from oracle import oracle_api
+
+    path = oracle_api.build_ref()
+    if path is None:
+        pytest.skip("oracle/_ref/librbis_ref.so is not built and /root/reference is not mounted")
+    ref = C.CDLL(path)
+    if not hasattr(ref, "orc_legodo_create_measurement"):
+        pytest.skip("oracle/_ref/librbis_ref.so predates the leg-odometry export")
+    vp = C.c_void_p
+    ref.orc_legodo_create_measurement.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_float, vp, vp, vp, vp, vp]
+    ref.orc_legodo_create_measurement.restype = C.c_int
+    exe = os.path.join(BUILD, "legodo_check")
+    os.makedirs(BUILD, exist_ok=True)
+    libdir = os.path.join(ROOT, "pronto_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-o", exe, os.path.join(ROOT, "tests", "cpp", "legodo_check.cpp"),
+                           f"-L{libdir}", "-lrbis_b200", f"-Wl,-rpath,{libdir}"])
+    rng = np.random.default_rng(11)
+    modes = {0: b"lin_rate", 2: b"lin_rot_rate", 3: b"pos_and_lin_rate"}
+    worst = 0.0
+    for case in range(60):
+        mode = [0, 2, 3][case % 3]
+        r = np.abs(rng.normal(size=5)) * 0.3 + 0.01
+        pos = rng.normal(size=3)
+        pq = rng.normal(size=4); pq /= np.linalg.norm(pq)
+        dxyz = rng.normal(size=3) * 0.01
+        ang = rng.normal(size=3) * (0.02 if case % 4 else 0.8)   # mostly small increments, some large rotations
+        n = np.linalg.norm(ang)
+        dq = np.concatenate([[np.cos(n / 2)], np.sin(n / 2) * ang / n])
+        prev = 1_000_000 + int(rng.integers(0, 1000))
+        ut = prev + int(rng.integers(500, 20000))
+        pos_ok, delta_status = int(rng.integers(0, 2)), float(rng.choice([0.0, 0.2, 0.5, 0.7, 1.0]))
+        m, ut_out = C.c_int(0), C.c_int64(0)
+        idx, z, cov = np.zeros(6, dtype=np.int32), np.zeros(6), np.zeros(36)
+        sensor = ref.orc_legodo_create_measurement(modes[mode], r.ctypes.data, pos.ctypes.data, pq.ctypes.data, dxyz.ctypes.data, dq.ctypes.data,
+                                                   ut, prev, pos_ok, delta_status, C.byref(m), idx.ctypes.data, z.ctypes.data, cov.ctypes.data,
+                                                   C.byref(ut_out))
+        args = [str(mode)] + [repr(float(v)) for v in r] + [str(ut), str(prev), str(pos_ok), repr(delta_status)] + \
+               [repr(float(v)) for v in np.concatenate([pos, dxyz, dq])]
+        line = subprocess.run([exe] + args, capture_output=True, text=True, check=True).stdout.strip()
+        f = dict(kv.split("=", 1) for kv in line.split(" ", 1)[1].split(" "))
+        k = m.value
+        assert int(f["m"]) == k and [int(v) for v in f["idx"].split(",") if v] == list(idx[:k]), (case, line)
+        assert int(f["sensor"]) == sensor and int(f["utime"]) == ut_out.value == ut
+        R_ref = cov[:k * k].reshape(k, k)
+        assert np.array_equal(np.diag(R_ref), [float(v) for v in f["Rdiag"].split(",") if v]) and float(f["offdiag"]) == 0.0
+        assert np.count_nonzero(R_ref - np.diag(np.diag(R_ref))) == 0
+        zz = np.array([float(v) for v in f["z"].split(",") if v])
+        err = np.max(np.abs(zz - z[:k]) / np.maximum(1.0, np.abs(z[:k])))
+        worst = max(worst, err)
+    assert worst <= 1e-12, worst
