@@ -121,3 +121,43 @@ def test_consecutive_synth_launches_overlap_safely():
     for o in out[1:]:
         for x, y in zip(out[0][:4], o[:4]):
             assert np.array_equal(x, y)
+
+
+def test_full_size_monte_carlo_ensemble_matches_oracle_on_scattered_filters(oracle):
+    """BASELINE configs[2] at full size: 65,536 DISTINCT filters (counter-based initial ensemble and sensor rows, drawn inside the
+    fused lane-per-filter kernel) through 300 steps of IMU + leg odometry + pose fixes; 384 filters scattered over the ensemble are
+    replayed by the CPU oracle from the rows the device drew for exactly those filters."""
+    import torch
+
+    N, T, S = 65536, 300, 384
+    truth = synth.truth_trajectory(T)
+    tv0 = np.zeros(21)
+    tv0[9:12] = (0, 0, 0.85); tv0[15:18] = synth.NOMINAL["bg"]; tv0[18:21] = synth.NOMINAL["ba"]
+    vec0, quat0, cov0 = synth.initial_ensemble(N, tv0, truth["quat"][0])
+    st1 = synth.make_streams(truth, 1, 0, T)
+    ev = st1["events"]
+    streams = [MeasStream(synth.LEGODO_IDX, None, st1["R_legodo"]), MeasStream(synth.POSE_IDX, None, st1["R_pose"], quat=True)]
+    pick = np.sort(np.random.default_rng(5).choice(N, size=S, replace=False))
+    with RBISBatch(N) as b:
+        b.set_process_noise(*nominal_q())
+        b.set_state(vec0, quat0, cov0)
+        spec = _spec(truth, 0, T, mode=1)
+        b.run_fused_synth(ev, streams, spec)
+        assert b.last_kernel_variant == 2 + 4      # decoupled lane-per-filter kernel, SYN instantiation
+        gv, gq, gP, gll, _ = b.get_state()
+        rows = b.synthesize(spec)
+        sel = torch.from_numpy(pick).to(rows["imu"].device)
+        take = lambda t: t.index_select(t.ndim - 1, sel).cpu().numpy()
+        imu, lz, pz, pq = take(rows["imu"]), take(rows["z"][0]), take(rows["z"][1]), take(rows["quat"][1])
+    assert np.isfinite(gv).all() and np.isfinite(gP).all()
+    sub = lambda a: np.ascontiguousarray(a[..., pick])
+    orc = oracle.run_ensemble(sub(vec0), sub(quat0), sub(cov0), None, 0, nominal_q(), imu,
+                              [dict(idx=synth.LEGODO_IDX, z=lz, R=st1["R_legodo"]), dict(idx=synth.POSE_IDX, z=pz, R=st1["R_pose"], quat=pq)],
+                              ev, n_threads=NTHREADS)
+    e = max_errors(sub(gv), sub(gq), sub(gP), orc["vec"], orc["quat"], orc["cov"])
+    assert max(e.values()) < 1e-9, e
+    assert np.max(np.abs(sub(gll) - orc["loglik"]) / np.maximum(1.0, np.abs(orc["loglik"]))) < 1e-9
+    # the ensemble is an ensemble: distinct filters, consistent with the truth
+    assert np.unique(gv[3]).size > 0.99 * N
+    tvT, _ = synth.truth_state_at(truth, T - 1)
+    assert np.sqrt(np.mean((gv[9:12] - tvT[9:12, None]) ** 2)) < 0.05
