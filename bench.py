@@ -628,25 +628,29 @@ def run_b200(args):
     n_local = (N + CHUNK - 1) // CHUNK
     if not args.no_e2e:
         b.close()
-        b = new_batch(N, dense_only=args.dense_only, piece_ops=100)
+        b = new_batch(N, dense_only=args.dense_only, piece_ops=100, snapshot_slots=2)
         stream = torch.cuda.ExternalStream(b.cuda_stream, device=dev)
         E = max(1, min(args.e2e_steps, K * L))
         ring = min(3, resident)
         host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in wl.chunks[c].items()} for c in range(ring)]
         torch.cuda.synchronize()
         hnp = [{k: v.numpy() for k, v in h.items()} for h in host]
-        hprep = [b.prepare_fused(wl.progs[c], imu=hnp[c]["imu"], streams=[MeasStream(synth.LEGODO_IDX, hnp[c]["legodo"], R_lego),
-                                                                          MeasStream(synth.POSE_IDX, hnp[c]["pose_z"], R_pose, quat=hnp[c]["pose_q"])])
-                 for c in range(ring)]
+        def with_snapshot(prog, slot):
+            """the step's last program also leaves the ensemble in ring slot `slot`, for the side-stream statistics"""
+            return np.concatenate([prog, make_ops([(capi.OP_SNAPSHOT, 0, slot, int(prog["utime"][-1]), 0.0)])])
+
+        hstreams = lambda c: [MeasStream(synth.LEGODO_IDX, hnp[c]["legodo"], R_lego), MeasStream(synth.POSE_IDX, hnp[c]["pose_z"], R_pose, quat=hnp[c]["pose_q"])]
+        hprep = [b.prepare_fused(wl.progs[c], imu=hnp[c]["imu"], streams=hstreams(c)) for c in range(ring)]
+        hprep_last = [[b.prepare_fused(with_snapshot(wl.progs[c], s_), imu=hnp[c]["imu"], streams=hstreams(c)) for s_ in range(2)] for c in range(ring)]
         res = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True) for _ in range(2)]
         resnp = [r.numpy() for r in res]
         b.set_state(wl.vec0, wl.quat0, wl.cov0)
 
         def e2e_step(i):
-            for j in range(L):
+            for j in range(L - 1):
                 b.run_prepared(hprep[(i * L + j) % ring])
-            b.stats_enqueue(tv, tq, resnp[i % 2], chunk=CHUNK)
-            return b.record()
+            b.run_prepared(hprep_last[(i * L + L - 1) % ring][i % 2])
+            return b.stats_snapshot_enqueue(i % 2, tv, tq, resnp[i % 2], chunk=CHUNK)
 
         tick = None
         for i in range(2):  # warm-up (allocates the staging buffers)
@@ -677,7 +681,8 @@ def run_b200(args):
         e2e = {"value": n_total * Tc * L * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": L * (wl.in_bytes + wl.progs[0].nbytes),
                "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": e2e_ms / E,
                "step": f"{L} fused launches ({Tc} trajectory steps of every filter each), every one with its own host->device input copy from pinned "
-                       "memory, then the statistics of the step read back on the host",
+                       "memory; the last one snapshots the ensemble, whose statistics are computed on a side stream and read back on the host "
+                       "(rbis_batch_stats_snapshot_enqueue) while the next step already runs",
                "bound": "PCIe: per-filter input rows cross the bus", "launches_per_step": (b.launch_count - l0) / E}
         del host, hnp, hprep
 
@@ -695,10 +700,10 @@ def run_b200(args):
         res_s = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
 
         def synth_step(i):
-            for j in range(L):
+            for j in range(L - 1):
                 b.run_fused_synth(wl.progs[(i * L + j) % resident], sstreams, specs[i * L + j])
-            b.stats_enqueue(tv, tq, res_s[i % 2], chunk=CHUNK)
-            return b.record()
+            b.run_fused_synth(with_snapshot(wl.progs[(i * L + L - 1) % resident], i % 2), sstreams, specs[i * L + L - 1])
+            return b.stats_snapshot_enqueue(i % 2, tv, tq, res_s[i % 2], chunk=CHUNK)
 
         b.set_state(wl.vec0, wl.quat0, wl.cov0)
         tick = None
@@ -731,8 +736,9 @@ def run_b200(args):
                      "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": syn_ms / E,
                      "launches_per_step": (b.launch_count - l0) / E, "generator": "splitmix64 counters -> Box-Muller, fast mode (rbis_synth_t::mode 1)",
                      "kernel_variant": variant_name(b.last_kernel_variant),
-                     "what": f"rbis_batch_run_fused_synth, {L} calls per step + statistics read-back: the host sends the noise-free rows and a seed, the "
-                             "fused kernel draws every filter's noisy rows itself (SYN instantiation) -- no per-filter input exists in HBM"}
+                     "what": f"rbis_batch_run_fused_synth, {L} calls per step + statistics read-back (of the snapshot the step's last program "
+                             "leaves, on a side stream): the host sends the noise-free rows and a seed, the fused kernel draws every filter's noisy "
+                             "rows itself (SYN instantiation) -- no per-filter input exists in HBM"}
         prof_s, why_s = kernel_profile(b.last_kernel_variant)
         if prof_s:
             ex_s = 2 * prof_s["dfma"] + prof_s["dmul"] + prof_s["dadd"]

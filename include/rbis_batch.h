@@ -348,6 +348,14 @@ int rbis_batch_stats(rbis_batch_t* h, const double* truth_vec, const double* tru
  * the next step. */
 int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const double* truth_quat, int chunk,
                              double* out_chunks, int64_t* n_chunks);
+/* The same statistics over SNAPSHOT SLOT `slot` (written by an RBIS_OP_SNAPSHOT of an earlier fused program) instead of the live
+ * ensemble, on a side stream: the pass is ordered after the launch that wrote the slot and nothing waits for it -- the fused
+ * launches that follow keep overlapping the ones before, which a read of the LIVE state (rbis_batch_stats_enqueue) prevents.
+ * A later program that snapshots into the same slot waits for this pass.  out_chunks must be PINNED host memory; it is valid
+ * once rbis_batch_wait(*ticket) returns.  This is how a Monte-Carlo driver reads the ensemble error / NEES every step of a long
+ * replay (append RBIS_OP_SNAPSHOT to the step's last program, alternate two slots) without draining the device. */
+int rbis_batch_stats_snapshot_enqueue(rbis_batch_t* h, int32_t slot, const double* truth_vec, const double* truth_quat, int chunk,
+                                      double* out_chunks, int64_t* n_chunks, int32_t* ticket);
 /* ---- statistics of a SHARDED ensemble: one process per GPU, each handle holds the contiguous filter range
  * [first_chunk * chunk, first_chunk * chunk + N) of an ensemble of total_chunks chunks.  The shard's chunk partials are written
  * into its rows of a zero-initialised DEVICE table [total_chunks][RBIS_NUM_STATS], the table is summed over the ranks with

@@ -449,6 +449,18 @@ class RBISBatch:
         nch = C.c_int64(0)
         capi.check(self.lib.rbis_batch_stats_enqueue(self.h, tv.ctypes.data, tq.ctypes.data, int(chunk), po, C.byref(nch)))
 
+    def stats_snapshot_enqueue(self, slot, truth_vec, truth_quat, out_chunks, chunk=1024):
+        """Statistics over snapshot slot `slot` on a side stream (rbis_batch_stats_snapshot_enqueue) into a PINNED host array
+        [n_chunks][96]; returns the ticket to wait() for.  The fused launches that follow do not wait for it."""
+        tv = np.ascontiguousarray(truth_vec, dtype=np.float64); tq = np.ascontiguousarray(truth_quat, dtype=np.float64)
+        assert tv.size == 21 and tq.size == 4
+        n_chunks = (self.N + chunk - 1) // chunk
+        po, _ = _ptr(out_chunks, (n_chunks, capi.NUM_STATS), "out_chunks")
+        nch, t = C.c_int64(0), C.c_int32(0)
+        capi.check(self.lib.rbis_batch_stats_snapshot_enqueue(self.h, int(slot), tv.ctypes.data, tq.ctypes.data, int(chunk), po, C.byref(nch),
+                                                              C.byref(t)))
+        return t.value
+
     def record(self):
         t = C.c_int32(0)
         capi.check(self.lib.rbis_batch_record(self.h, C.byref(t)))

@@ -155,6 +155,12 @@ struct rbis_batch {
   bool stream_dirty = true;   // the main stream got work since the last grouped launch
   cudaEvent_t tickets[8] = {};
   int next_ticket = 0;
+  // ---- statistics over a snapshot slot on a side stream (rbis_batch_stats_snapshot_enqueue): the fused launches that follow do
+  // not wait for it; a launch that REWRITES the slot waits for the slot's last reader
+  cudaStream_t stats_stream = nullptr;
+  std::vector<cudaEvent_t> snap_read_evt;   // per slot, created on first use
+  std::vector<char> snap_read_pending;
+  std::vector<DevBuf> snap_stats_scratch;   // per slot: truth [25] + chunk partials
   int smem_bytes = 0;
 };
 
@@ -661,8 +667,18 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (staging) CUDA_TRY(cudaEventRecord(slot.copied, cst));
   const LaunchGeom geom = launch_geom(variant, h->mapping, h->lane_tpb, N, h->n_sms);
   const unsigned grid = geom.grid;
+  // slots this program overwrites that a side-stream statistics pass may still be reading
+  std::vector<cudaEvent_t> slot_readers;
+  if (any_snapshot && !h->snap_read_pending.empty()) {
+    for (int64_t i = 0; i < n_ops; i++)
+      if (ops[i].kind == RBIS_OP_SNAPSHOT && h->snap_read_pending[(size_t)ops[i].row]) {
+        slot_readers.push_back(h->snap_read_evt[(size_t)ops[i].row]);
+        h->snap_read_pending[(size_t)ops[i].row] = 0;
+      }
+  }
   if (!grouped) {
     if (int rc = main_stream_work(h)) return rc;
+    for (cudaEvent_t e : slot_readers) CUDA_TRY(cudaStreamWaitEvent(h->stream, e, 0));
     if (staging) CUDA_TRY(cudaStreamWaitEvent(h->stream, slot.copied, 0));
     // ---- op table and shared R matrices (small, pageable source: staged synchronously by the runtime) ----
     if ((size_t)n_ops > h->d_ops_cap) {
@@ -745,6 +761,8 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
         if (repartitioned)
           for (int g2 = 0; g2 < h->n_groups; g2++) CUDA_TRY(cudaStreamWaitEvent(gs, h->gdone[h->last_ring][g2], 0));
         if (wait_main) CUDA_TRY(cudaStreamWaitEvent(gs, h->pre_evt, 0));
+        if (pc == 0)
+          for (cudaEvent_t e : slot_readers) CUDA_TRY(cudaStreamWaitEvent(gs, e, 0));
         if (staging && pc == 0) CUDA_TRY(cudaStreamWaitEvent(gs, slot.copied, 0));
         CUDA_TRY(cudaStreamWaitEvent(gs, h->uploaded[ring], 0));
         if (b1 > b0) {
@@ -945,6 +963,9 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   h->notch_stage.release();
   for (auto& m : h->d_map) cudaFree(m);
   h->full_cov.release(); h->misc.release(); h->stats_async.release(); h->stats_table.release(); h->synth_small.release(); h->d_syn.release();
+  for (auto& b : h->snap_stats_scratch) b.release();
+  for (cudaEvent_t e : h->snap_read_evt) if (e) cudaEventDestroy(e);
+  if (h->stats_stream) cudaStreamDestroy(h->stats_stream);
   for (auto& b : h->d_syn_ring) b.release();
   for (auto& s : h->slots) {
     s.imu.release();
@@ -1318,6 +1339,60 @@ int rbis_batch_stats_enqueue(rbis_batch_t* h, const double* truth_vec, const dou
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   CUDA_TRY(cudaMemcpyAsync(out_chunks, d_chunks, (size_t)nch * RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (n_chunks) *n_chunks = nch;
+  return 0;
+}
+
+int rbis_batch_stats_snapshot_enqueue(rbis_batch_t* h, int32_t slot, const double* truth_vec, const double* truth_quat, int chunk,
+                                      double* out_chunks, int64_t* n_chunks, int32_t* ticket) {
+  if (!h) return fail(RBIS_ERR_INVALID, "null handle");
+  if (!truth_vec || !truth_quat || !out_chunks || !ticket) return fail(RBIS_ERR_INVALID, "truth, out_chunks and ticket are required");
+  if (chunk < 32 || chunk > 1024 || (chunk & (chunk - 1))) return fail(RBIS_ERR_INVALID, "chunk must be a power of two in [32,1024]");
+  const int S = h->cfg.snapshot_slots;
+  if (slot < 0 || slot >= S) return fail(RBIS_ERR_INVALID, "snapshot slot %d out of range (%d slots)", slot, S);
+  if (!h->snap_valid[(size_t)slot]) return fail(RBIS_ERR_STATE, "snapshot slot %d is empty", slot);
+  if (int rc = use_device(h)) return rc;
+  if (!h->stats_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stats_stream, cudaStreamNonBlocking));
+    h->snap_read_evt.assign((size_t)S, nullptr);
+    h->snap_read_pending.assign((size_t)S, 0);
+    h->snap_stats_scratch.resize((size_t)S);
+  }
+  if (!h->snap_read_evt[(size_t)slot]) CUDA_TRY(cudaEventCreateWithFlags(&h->snap_read_evt[(size_t)slot], cudaEventDisableTiming));
+  const size_t N = (size_t)h->N;
+  const int64_t nch = (int64_t)((N + chunk - 1) / chunk);
+  cudaStream_t ss = h->stats_stream;
+  // after whatever wrote the slot: the group streams of the last fused launch, or the main stream; the main stream is NOT
+  // made to join anything, so the fused launches that follow keep overlapping the ones before
+  if (h->groups_dirty) {
+    for (int g = 0; g < h->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(ss, h->gdone[h->last_ring][g], 0));
+  }
+  if (!h->syn_evt) CUDA_TRY(cudaEventCreateWithFlags(&h->syn_evt, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(h->syn_evt, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ss, h->syn_evt, 0));
+  DevBuf& scratch = h->snap_stats_scratch[(size_t)slot];
+  if (scratch.cap < 25 + (size_t)nch * RBIS_NUM_STATS) {
+    if (h->snap_read_pending[(size_t)slot]) CUDA_TRY(cudaEventSynchronize(h->snap_read_evt[(size_t)slot]));
+    if (scratch.ensure(25 + (size_t)nch * RBIS_NUM_STATS)) return fail(RBIS_ERR_ALLOC, "scratch allocation failed");
+  }
+  double* d_truth = scratch.p;
+  double* d_chunks = d_truth + 25;
+  double tbuf[25];
+  std::memcpy(tbuf, truth_vec, 21 * sizeof(double));
+  std::memcpy(tbuf + 21, truth_quat, 4 * sizeof(double));
+  if (int rc = upload_small(h, d_truth, tbuf, sizeof(tbuf), ss)) return rc;
+  const double* d = h->snap + (size_t)slot * rbisk::SNAP_ROWS * N;  // [257][N]: vec 0..20, quat 21..24, loglik 25, packed covariance 26..
+  rbisk::stats_kernel<<<(unsigned)nch, chunk, chunk * sizeof(double), ss>>>(d, d + 21 * N, d + 26 * N, d + 25 * N, d_truth, d_truth + 21, 0,
+                                                                            (long long)N, nullptr, d_chunks);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out_chunks, d_chunks, (size_t)nch * RBIS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, ss));
+  CUDA_TRY(cudaEventRecord(h->snap_read_evt[(size_t)slot], ss));
+  h->snap_read_pending[(size_t)slot] = 1;
+  const int t = h->next_ticket;
+  h->next_ticket = (t + 1) % 8;
+  CUDA_TRY(cudaEventRecord(h->tickets[t], ss));
+  *ticket = t;
   if (n_chunks) *n_chunks = nch;
   return 0;
 }

@@ -676,3 +676,39 @@ def test_single_updates_match_reference_golden(ref_golden):
             assert np.max(np.abs(gq - g[f"m{c}_quat"][:, None])) < 1e-11, c
             assert np.max(np.abs(gP - g[f"m{c}_cov"].T.reshape(-1)[:, None])) < 1e-12, c
             assert np.max(np.abs(gll - float(g[f"m{c}_ll"]))) < 1e-9 * max(1.0, abs(float(g[f"m{c}_ll"]))), c
+
+
+def test_snapshot_statistics_on_the_side_stream_equal_live_statistics():
+    """rbis_batch_stats_snapshot_enqueue: the statistics of the ensemble as the program's final SNAPSHOT left it, computed on a side
+    stream while later launches already run -- same bits as rbis_batch_stats on the live state at that point, for launch groups
+    on and off, and a program that re-snapshots into the slot waits for the reader."""
+    import torch
+
+    N, T, CH = 3000, 60, 256
+    sc = scenario(N, T)
+    st = sc["st"]
+    ev = list(st["events"])
+    half = len(ev) // 2
+    tv, tq = synth.truth_state_at(sc["truth"], T - 1)
+    n_ch = (N + CH - 1) // CH
+    for groups in (1, 4):
+        with RBISBatch(N, snapshot_slots=2, launch_groups=groups, mapping=1) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            b.run_fused(ev[:half], imu=st["imu"], streams=gpu_streams(st))
+            want_a, _ = b.stats(tv, tq, chunk=CH)
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            outs = [torch.empty((n_ch, capi.NUM_STATS), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
+            b.run_fused(ev[:half] + [(capi.OP_SNAPSHOT, 0, 0, ev[half - 1][3], 0.0)], imu=st["imu"], streams=gpu_streams(st))
+            t0 = b.stats_snapshot_enqueue(0, tv, tq, outs[0], chunk=CH)
+            # the ensemble moves on at once; the second half ends with a snapshot into slot 1, a third launch re-snapshots slot 0
+            b.run_fused(ev[half:] + [(capi.OP_SNAPSHOT, 0, 1, ev[-1][3], 0.0)], imu=st["imu"], streams=gpu_streams(st))
+            t1 = b.stats_snapshot_enqueue(1, tv, tq, outs[1], chunk=CH)
+            b.run_fused([(capi.OP_SNAPSHOT, 0, 0, ev[-1][3], 0.0)], imu=st["imu"], streams=gpu_streams(st))
+            t2 = b.stats_snapshot_enqueue(0, tv, tq, outs[2], chunk=CH)
+            for t in (t0, t1, t2):
+                b.wait(t)
+            want_b, _ = b.stats(tv, tq, chunk=CH)
+        assert np.array_equal(outs[0], want_a), groups
+        assert np.array_equal(outs[1], want_b) and np.array_equal(outs[2], want_b), groups
+        assert not np.array_equal(want_a, want_b)
