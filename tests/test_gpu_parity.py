@@ -712,3 +712,14 @@ def test_snapshot_statistics_on_the_side_stream_equal_live_statistics():
         assert np.array_equal(outs[0], want_a), groups
         assert np.array_equal(outs[1], want_b) and np.array_equal(outs[2], want_b), groups
         assert not np.array_equal(want_a, want_b)
+    # argument checking: slots out of range / never written, a handle without a ring
+    from pronto_b200.capi import RBISError
+
+    with RBISBatch(64, snapshot_slots=2) as b:
+        out = torch.empty((1, capi.NUM_STATS), dtype=torch.float64, pin_memory=True).numpy()
+        for bad in (-1, 2, 1):   # 1 is in range but empty
+            with pytest.raises(RBISError):
+                b.stats_snapshot_enqueue(bad, tv, tq, out, chunk=64)
+    with RBISBatch(64) as b:
+        with pytest.raises(RBISError):
+            b.stats_snapshot_enqueue(0, tv, tq, out, chunk=64)
