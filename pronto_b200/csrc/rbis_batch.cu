@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -989,6 +990,10 @@ int rbis_batch_synchronize(rbis_batch_t* h) {
   CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
   if (h->upload_stream) CUDA_TRY(cudaStreamSynchronize(h->upload_stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->stats_stream) {  // side-stream statistics (rbis_batch_stats_snapshot_enqueue): done too, their slots are free again
+    CUDA_TRY(cudaStreamSynchronize(h->stats_stream));
+    std::fill(h->snap_read_pending.begin(), h->snap_read_pending.end(), 0);
+  }
   return 0;
 }
 
