@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""dev/sanitize_case.py -- one small pass through every fused-kernel family, for compute-sanitizer (memcheck / racecheck / synccheck):
+"""dev/all_kernels_check.py -- one small pass through every fused-kernel family with a bit-identity check (compute-sanitizer is closed on the GPU pool):
 lane-per-filter decoupled + dense, warp-group 4 / 8 lanes, SYN instantiations, snapshot / restore, snapshot statistics."""
 import os, sys
 import numpy as np
