@@ -624,67 +624,74 @@ def run_b200(args):
     # host->device input copy) followed by the read-back of the step's statistics on the host ----
     # Reading a result keeps the calls on either side of it from overlapping, so these legs run on a handle whose calls are
     # cut into pieces of ~100 ops (rbis_batch_config_t::piece_ops): the partially filled last wave of one piece overlaps the next.
-    e2e = None
+    e2e = e2e_f32 = None
     n_local = (N + CHUNK - 1) // CHUNK
     if not args.no_e2e:
         b.close()
         b = new_batch(N, dense_only=args.dense_only, piece_ops=100, snapshot_slots=2)
         stream = torch.cuda.ExternalStream(b.cuda_stream, device=dev)
-        E = max(1, min(args.e2e_steps, K * L))
-        ring = min(3, resident)
-        host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in wl.chunks[c].items()} for c in range(ring)]
-        torch.cuda.synchronize()
-        hnp = [{k: v.numpy() for k, v in h.items()} for h in host]
         def with_snapshot(prog, slot):
             """the step's last program also leaves the ensemble in ring slot `slot`, for the side-stream statistics"""
             return np.concatenate([prog, make_ops([(capi.OP_SNAPSHOT, 0, slot, int(prog["utime"][-1]), 0.0)])])
 
-        hstreams = lambda c: [MeasStream(synth.LEGODO_IDX, hnp[c]["legodo"], R_lego), MeasStream(synth.POSE_IDX, hnp[c]["pose_z"], R_pose, quat=hnp[c]["pose_q"])]
-        hprep = [b.prepare_fused(wl.progs[c], imu=hnp[c]["imu"], streams=hstreams(c)) for c in range(ring)]
-        hprep_last = [[b.prepare_fused(with_snapshot(wl.progs[c], s_), imu=hnp[c]["imu"], streams=hstreams(c)) for s_ in range(2)] for c in range(ring)]
-        res = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        resnp = [r.numpy() for r in res]
-        b.set_state(wl.vec0, wl.quat0, wl.cov0)
+        def host_e2e(rows_dtype):
+            """rows_dtype None: the chunks as they are (float64); torch.float32: the same rows rounded to float and passed as float
+            arrays (RBIS_MEM_F32_ROWS: widened exactly on the device, half the PCIe bytes)"""
+            E = max(1, min(args.e2e_steps, K * L))
+            ring = min(3, resident)
+            host = [{k: torch.empty(v.shape, dtype=rows_dtype or v.dtype, pin_memory=True).copy_(v) for k, v in wl.chunks[c].items()} for c in range(ring)]
+            torch.cuda.synchronize()
+            hnp = [{k: v.numpy() for k, v in h.items()} for h in host]
+            hstreams = lambda c: [MeasStream(synth.LEGODO_IDX, hnp[c]["legodo"], R_lego), MeasStream(synth.POSE_IDX, hnp[c]["pose_z"], R_pose, quat=hnp[c]["pose_q"])]
+            hprep = [b.prepare_fused(wl.progs[c], imu=hnp[c]["imu"], streams=hstreams(c)) for c in range(ring)]
+            hprep_last = [[b.prepare_fused(with_snapshot(wl.progs[c], s_), imu=hnp[c]["imu"], streams=hstreams(c)) for s_ in range(2)] for c in range(ring)]
+            res = [torch.empty((n_local, capi.NUM_STATS), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            resnp = [r.numpy() for r in res]
+            b.set_state(wl.vec0, wl.quat0, wl.cov0)
 
-        def e2e_step(i):
-            for j in range(L - 1):
-                b.run_prepared(hprep[(i * L + j) % ring])
-            b.run_prepared(hprep_last[(i * L + L - 1) % ring][i % 2])
-            return b.stats_snapshot_enqueue(i % 2, tv, tq, resnp[i % 2], chunk=CHUNK)
+            def e2e_step(i):
+                for j in range(L - 1):
+                    b.run_prepared(hprep[(i * L + j) % ring])
+                b.run_prepared(hprep_last[(i * L + L - 1) % ring][i % 2])
+                return b.stats_snapshot_enqueue(i % 2, tv, tq, resnp[i % 2], chunk=CHUNK)
 
-        tick = None
-        for i in range(2):  # warm-up (allocates the staging buffers)
-            t = e2e_step(i)
-            if tick is not None:
-                b.wait(tick)
-            tick = t
-        b.wait(tick)
-        barrier()
-        b.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = b.launch_count
-        e0.record(stream)
-        tick, acc = None, 0.0
-        for i in range(E):
-            t = e2e_step(i)
-            if tick is not None:
-                b.wait(tick)
-                acc += float(resnp[(i - 1) % 2][0, 46])  # the launch's result is read on the host
-            tick = t
-        b.wait(tick)
-        acc += float(resnp[(E - 1) % 2][0, 46])
-        e1.record(stream)
-        barrier()
-        b.synchronize()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-        assert acc == E * min(CHUNK, N)
-        e2e = {"value": n_total * Tc * L * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": L * (wl.in_bytes + wl.progs[0].nbytes),
-               "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": e2e_ms / E,
-               "step": f"{L} fused launches ({Tc} trajectory steps of every filter each), every one with its own host->device input copy from pinned "
-                       "memory; the last one snapshots the ensemble, whose statistics are computed on a side stream and read back on the host "
-                       "(rbis_batch_stats_snapshot_enqueue) while the next step already runs",
-               "bound": "PCIe: per-filter input rows cross the bus", "launches_per_step": (b.launch_count - l0) / E}
-        del host, hnp, hprep
+            tick = None
+            for i in range(2):  # warm-up (allocates the staging buffers)
+                t = e2e_step(i)
+                if tick is not None:
+                    b.wait(tick)
+                tick = t
+            b.wait(tick)
+            barrier()
+            b.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = b.launch_count
+            e0.record(stream)
+            tick, acc = None, 0.0
+            for i in range(E):
+                t = e2e_step(i)
+                if tick is not None:
+                    b.wait(tick)
+                    acc += float(resnp[(i - 1) % 2][0, 46])  # the launch's result is read on the host
+                tick = t
+            b.wait(tick)
+            acc += float(resnp[(E - 1) % 2][0, 46])
+            e1.record(stream)
+            barrier()
+            b.synchronize()
+            e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+            assert acc == E * min(CHUNK, N)
+            return {"value": n_total * Tc * L * E / (e2e_ms * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": L * (sum(int(v.numel() * v.element_size()) for v in host[0].values()) + wl.progs[0].nbytes),
+                   "d2h_bytes_per_step": n_local * capi.NUM_STATS * 8, "steps": E, "ms_per_step": e2e_ms / E,
+                   "step": f"{L} fused launches ({Tc} trajectory steps of every filter each), every one with its own host->device input copy from pinned "
+                           "memory; the last one snapshots the ensemble, whose statistics are computed on a side stream and read back on the host "
+                           "(rbis_batch_stats_snapshot_enqueue) while the next step already runs",
+                   "bound": "PCIe: per-filter input rows cross the bus", "launches_per_step": (b.launch_count - l0) / E}
+        e2e = host_e2e(None)
+        e2e_f32 = host_e2e(torch.float32)
+        e2e_f32["what"] = ("the same steps with the sensor rows rounded to float32 and passed as float arrays (RBIS_MEM_F32_ROWS): widened exactly on "
+                           "the device, half the bytes over PCIe; a different ensemble from `e2e` only in that rounding of its inputs")
 
     # ---- e2e_synth: the Monte-Carlo form of the call -- noise-free rows + seed from the host, noise drawn on the device ----
     e2e_synth = None
@@ -1164,7 +1171,7 @@ def run_b200(args):
                        "l2_policy": f"every launch reads a fresh {BYTES_PER_STEP * N * Tc / 1e6:.0f} MB input chunk (L2 is 126 MB); {resident} of {n_launches} chunks resident in HBM"
                                     + ("" if resident == n_launches else " (cycled)"),
                        "stats_allreduce": ("rbis_batch_stats_allreduce over ncclComm_t, inside the timed region" if world > 1 else "single GPU, inside the timed region")},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_synth": e2e_synth, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32_rows": e2e_f32, "e2e_synth": e2e_synth, "gpu_launches": launches, "clocks": clocks,
             "ensemble": {"mean_nees9": summ["mean_nees"], "nees_in_95pct": summ["nees_in_95pct"], "non_finite": summ["non_finite"], "stats_sha256_16": stats_sha},
         }
         line.update(legs)

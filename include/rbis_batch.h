@@ -57,7 +57,14 @@ typedef enum {
   RBIS_ERR_STATE = -4     /* call sequence error (e.g. restore of an empty snapshot slot) */
 } rbis_status_t;
 
-typedef enum { RBIS_MEM_HOST = 0, RBIS_MEM_DEVICE = 1 } rbis_mem_t;
+typedef enum {
+  RBIS_MEM_HOST = 0,
+  RBIS_MEM_DEVICE = 1,
+  /* rbis_batch_run_fused only, OR-ed with one of the above: the sensor rows (imu, z, quat) are FLOAT arrays of the same shapes.  They
+   * are widened to double exactly on the device, so the results equal those of the same values passed as doubles; a host log that is
+   * float-valued (most sensor data is) then crosses PCIe in half the bytes.  Per-filter R arrays stay double. */
+  RBIS_MEM_F32_ROWS = 4
+} rbis_mem_t;
 
 /* Fused-program op kinds. */
 typedef enum {

@@ -37,6 +37,19 @@ def _ptr(a, shape=None, name="array"):
     return a.ctypes.data, capi.MEM_HOST
 
 
+def _ptr_rows(a, name):
+    """(address, mem, is_f32) of a sensor-row array for run_fused: float64 or float32, numpy or torch."""
+    if _is_torch(a):
+        import torch
+
+        if a.dtype not in (torch.float64, torch.float32) or not a.is_contiguous():
+            raise ValueError(f"{name}: need a contiguous float64 or float32 tensor")
+        return a.data_ptr(), (capi.MEM_DEVICE if a.is_cuda else capi.MEM_HOST), a.dtype == torch.float32
+    if not isinstance(a, np.ndarray) or a.dtype not in (np.float64, np.float32) or not a.flags.c_contiguous:
+        raise ValueError(f"{name}: need a C-contiguous float64 or float32 numpy array")
+    return a.ctypes.data, capi.MEM_HOST, a.dtype == np.float32
+
+
 def _common_mem(mems, what):
     mems = [m for m in mems if m is not None]
     if not mems:
@@ -292,13 +305,13 @@ class RBISBatch:
         if not (isinstance(ops, np.ndarray) and ops.dtype == OP_DTYPE):
             ops = make_ops(ops)
         ops = np.ascontiguousarray(ops)
-        mems = []
+        mems, f32s = [], []
         p_imu, imu_rows = None, 0
         if imu is not None:
             if imu.ndim != 3 or tuple(imu.shape[1:]) != (6, self._ncols(-1)):
                 raise ValueError("imu must be [rows][6][N] ([rows][6][cols] under a column map)")
-            p_imu, mm = _ptr(imu, name="imu")
-            imu_rows = int(imu.shape[0]); mems.append(mm)
+            p_imu, mm, f = _ptr_rows(imu, "imu")
+            imu_rows = int(imu.shape[0]); mems.append(mm); f32s.append(f)
         sarr = (capi.Stream * max(1, len(streams)))()
         keep = [ops, imu]
         for s, st in enumerate(streams):
@@ -311,11 +324,11 @@ class RBISBatch:
             if st.z.ndim != 3 or tuple(st.z.shape[1:]) != (m, self._ncols(s)):
                 raise ValueError(f"stream {s}: z must be [rows][{m}][N] (cols under a column map)")
             d.rows = int(st.z.shape[0])
-            d.z, mm = _ptr(st.z, name="z"); mems.append(mm)
+            d.z, mm, f = _ptr_rows(st.z, "z"); mems.append(mm); f32s.append(f)
             if st.quat is not None:
                 if tuple(st.quat.shape) != (d.rows, 4, self._ncols(s)):
                     raise ValueError(f"stream {s}: quat must be [rows][4][N] (cols under a column map)")
-                d.quat, mm = _ptr(st.quat, name="quat"); mems.append(mm)
+                d.quat, mm, f = _ptr_rows(st.quat, "quat"); mems.append(mm); f32s.append(f)
             if st.per_filter_diag:
                 d.R, mm = _ptr(st.R, (m, self.N), "R"); mems.append(mm)
             else:
@@ -324,6 +337,10 @@ class RBISBatch:
                 d.R = R.ctypes.data
             keep.append(st)
         mem = _common_mem(mems, "run_fused")
+        if f32s and any(f32s):
+            if not all(f32s):
+                raise ValueError("run_fused: the sensor rows (imu, z, quat) of one call must all be float64 or all float32")
+            mem |= capi.MEM_F32_ROWS   # float rows: widened exactly on the device (rbis_mem_t)
         return (len(ops), ops.ctypes.data_as(C.POINTER(capi.Op)), p_imu, imu_rows, len(streams), sarr, mem, keep)
 
     def run_prepared(self, prep):

@@ -16,6 +16,7 @@ MAX_STREAMS = 8
 NUM_STATS = 96
 
 MEM_HOST, MEM_DEVICE = 0, 1
+MEM_F32_ROWS = 4  # rbis_batch_run_fused: imu / z / quat are float32 arrays (widened exactly on the device)
 OP_IMU, OP_MEAS, OP_SNAPSHOT, OP_RESTORE = 0, 1, 2, 3
 R_SHARED_FULL, R_PER_FILTER_DIAG = 0, 1
 

@@ -68,6 +68,7 @@ struct DevBuf {  // grow-only device buffer
 struct StagingSlot {  // device copies of caller-host input arrays for one fused run
   DevBuf imu;
   DevBuf z[RBIS_MAX_STREAMS], quat[RBIS_MAX_STREAMS], rdiag[RBIS_MAX_STREAMS];
+  DevBuf f32;  // RBIS_MEM_F32_ROWS: device copy of the host float rows of one call (all arrays back to back), widened into the above
   cudaEvent_t copied = nullptr, consumed = nullptr;
   int ring = -1;  // grouped launches: ring slot whose group events mark the consumption of this staging slot
 };
@@ -402,6 +403,35 @@ int copy_in(rbis_batch* h, DevBuf& buf, const double* src, size_t count, int mem
   return 0;
 }
 
+// RBIS_MEM_F32_ROWS: float rows -> the double staging array (exact), on the copy stream
+__global__ void widen_rows_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    reinterpret_cast<double2*>(out + i)[0] = make_double2((double)v.x, (double)v.y);
+    reinterpret_cast<double2*>(out + i)[1] = make_double2((double)v.z, (double)v.w);
+  } else {
+    for (size_t k = i; k < n; k++) out[k] = (double)in[k];
+  }
+}
+// f32_base / f32_off: the call's float scratch (device) and the running offset in floats (kept a multiple of 4)
+int copy_in_f32(rbis_batch* h, DevBuf& buf, const void* src, size_t count, int mem, cudaStream_t st, float* f32_base, size_t* f32_off,
+                const double** out) {
+  if (buf.ensure(count)) return fail(RBIS_ERR_ALLOC, "device staging allocation of %zu doubles failed", count);
+  const float* dsrc = static_cast<const float*>(src);
+  if (mem == RBIS_MEM_HOST) {
+    float* d = f32_base + *f32_off;
+    CUDA_TRY(cudaMemcpyAsync(d, src, count * sizeof(float), cudaMemcpyHostToDevice, st));
+    *f32_off += (count + 3) & ~(size_t)3;
+    dsrc = d;
+  }
+  widen_rows_kernel<<<(unsigned)((count + 1023) / 1024), 256, 0, st>>>(dsrc, buf.p, count);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  *out = buf.p;
+  return 0;
+}
+
 int validate_stream(int s, const rbis_stream_t& in) {
   if (in.m < 1 || in.m > RBIS_MAX_MEAS) return fail(RBIS_ERR_INVALID, "stream %d: m=%d out of range", s, in.m);
   for (int a = 0; a < in.m; a++)
@@ -426,7 +456,10 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   if (!h) return fail(RBIS_ERR_INVALID, "null handle");
   if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(RBIS_ERR_INVALID, "bad op list");
   if (n_streams < 0 || n_streams > RBIS_MAX_STREAMS) return fail(RBIS_ERR_INVALID, "n_streams out of range");
+  const bool f32_rows = (mem & RBIS_MEM_F32_ROWS) != 0;
+  mem &= ~RBIS_MEM_F32_ROWS;
   if (mem != RBIS_MEM_HOST && mem != RBIS_MEM_DEVICE) return fail(RBIS_ERR_INVALID, "bad mem");
+  if (f32_rows && syn) return fail(RBIS_ERR_INVALID, "RBIS_MEM_F32_ROWS does not apply to synthesised inputs");
   if (n_ops == 0) return 0;
   if (int rc = use_device(h)) return rc;
   const int64_t N = h->N;
@@ -615,7 +648,7 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
   // ---- inputs: stage host arrays on the copy stream (double buffered), or use device arrays in place ----
   StagingSlot& slot = h->slots[h->slot_toggle];
   cudaStream_t cst = h->copy_stream;
-  const bool staging = ((mem == RBIS_MEM_HOST) || syn != nullptr) && !fuse_syn;
+  const bool staging = ((mem == RBIS_MEM_HOST) || syn != nullptr || f32_rows) && !fuse_syn;
   const bool grouped = h->n_groups > 1;
   if (staging) {
     h->slot_toggle ^= 1;
@@ -649,14 +682,32 @@ int launch_fused(rbis_batch* h, int64_t n_ops, const rbis_op_t* ops, const doubl
     if (int rc = synthesize_into(h, syn, slot.imu.p, z_out, q_out, cst)) return rc;
     imu = slot.imu.p;
   }
+  // RBIS_MEM_F32_ROWS with host rows: one float scratch for all arrays of the call
+  size_t f32_off = 0;
+  if (f32_rows && mem == RBIS_MEM_HOST) {
+    size_t total = imu ? (((size_t)imu_rows * 6 * (size_t)kp.imu_cols + 3) & ~(size_t)3) : 0;
+    for (int s = 0; s < n_streams; s++) {
+      const size_t cols = (size_t)kp.streams[s].cols;
+      total += ((size_t)streams[s].rows * streams[s].m * cols + 3) & ~(size_t)3;
+      if (streams[s].has_orientation) total += ((size_t)streams[s].rows * 4 * cols + 3) & ~(size_t)3;
+    }
+    if (slot.f32.ensure((total + 1) / 2)) return fail(RBIS_ERR_ALLOC, "device staging allocation failed");
+  }
+  float* const f32_base = reinterpret_cast<float*>(slot.f32.p);
   if (imu && !fuse_syn) {
-    if (int rc = copy_in(h, slot.imu, imu, (size_t)imu_rows * 6 * (size_t)kp.imu_cols, mem, cst, &kp.imu)) return rc;
+    const size_t cnt = (size_t)imu_rows * 6 * (size_t)kp.imu_cols;
+    if (f32_rows) { if (int rc = copy_in_f32(h, slot.imu, imu, cnt, mem, cst, f32_base, &f32_off, &kp.imu)) return rc; }
+    else if (int rc = copy_in(h, slot.imu, imu, cnt, mem, cst, &kp.imu)) return rc;
   }
   for (int s = 0; s < n_streams; s++) {
     const rbis_stream_t& in = streams[s];
     rbisk::StreamDesc& d = kp.streams[s];
     if (in.rows == 0) continue;
-    if (!fuse_syn) {
+    if (!fuse_syn && f32_rows) {
+      if (int rc = copy_in_f32(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, f32_base, &f32_off, &d.z)) return rc;
+      if (in.has_orientation)
+        if (int rc = copy_in_f32(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, f32_base, &f32_off, &d.quat)) return rc;
+    } else if (!fuse_syn) {
       if (int rc = copy_in(h, slot.z[s], in.z, (size_t)in.rows * in.m * (size_t)d.cols, mem, cst, &d.z)) return rc;
       if (in.has_orientation)
         if (int rc = copy_in(h, slot.quat[s], in.quat, (size_t)in.rows * 4 * (size_t)d.cols, mem, cst, &d.quat)) return rc;
@@ -969,7 +1020,7 @@ int rbis_batch_destroy(rbis_batch_t* h) {
   if (h->stats_stream) cudaStreamDestroy(h->stats_stream);
   for (auto& b : h->d_syn_ring) b.release();
   for (auto& s : h->slots) {
-    s.imu.release();
+    s.imu.release(); s.f32.release();
     for (int i = 0; i < RBIS_MAX_STREAMS; i++) { s.z[i].release(); s.quat[i].release(); s.rdiag[i].release(); }
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);

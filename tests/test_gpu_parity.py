@@ -723,3 +723,33 @@ def test_snapshot_statistics_on_the_side_stream_equal_live_statistics():
     with RBISBatch(64) as b:
         with pytest.raises(RBISError):
             b.stats_snapshot_enqueue(0, tv, tq, out, chunk=64)
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_float32_rows_are_widened_exactly(where):
+    """RBIS_MEM_F32_ROWS: sensor rows given as float arrays (host: half the PCIe bytes) give the same bits as the same values given as
+    doubles, with and without launch groups."""
+    import torch
+
+    N, T = 1500, 40
+    sc = scenario(N, T)
+    st = sc["st"]
+    f32 = {k: np.ascontiguousarray(st[k].astype(np.float32)) for k in ("imu", "legodo", "pose_z", "pose_q")}
+    f64 = {k: np.ascontiguousarray(v.astype(np.float64)) for k, v in f32.items()}
+    put = (lambda a: torch.from_numpy(a).cuda()) if where == "device" else (lambda a: a)
+    out = []
+    for rows, groups in ((f64, 1), (f32, 1), (f32, 3)):
+        with RBISBatch(N, launch_groups=groups, mapping=1) as b:
+            b.set_process_noise(*nominal_q())
+            b.set_state(sc["vec"], sc["quat"], sc["cov"])
+            r = {k: put(v) for k, v in rows.items()}
+            ev = st["events"]
+            h = len(ev) // 2
+            for part in (ev[:h], ev[h:]):   # two calls: the float scratch of the staging slots is reused
+                b.run_fused(part, imu=r["imu"], streams=[MeasStream(synth.LEGODO_IDX, r["legodo"], st["R_legodo"]),
+                                                         MeasStream(synth.POSE_IDX, r["pose_z"], st["R_pose"], quat=r["pose_q"])])
+            out.append(b.get_state())
+    for o in out[1:]:
+        for x, y in zip(out[0][:4], o[:4]):
+            assert np.array_equal(x, y)
+    assert np.isfinite(out[0][0]).all()
